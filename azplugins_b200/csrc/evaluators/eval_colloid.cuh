@@ -1,0 +1,210 @@
+// eval_colloid.cuh -- integrated Lennard-Jones ("colloid") potential with three couplings chosen
+// by the radii of the type pair: point-point, sphere-point, sphere-sphere (Everaers-Ejtehadi).
+// Behaviour: reference src/PairEvaluatorColloid.h:23-57 (param_type), :101-113 (solvent-solvent),
+// :125-152 (colloid-solvent), :164-220 (colloid-colloid), :233-269 (dispatch, shift).
+//
+// The coupling is a property of the type pair, so it is resolved once in make_cache (with the
+// energy at r_cut) instead of by three radius comparisons per neighbour. The sphere-sphere
+// branch suffers catastrophic cancellation in fp32 (differences of k^-7 terms); it is rare
+// (colloid-colloid contacts) and is therefore evaluated with IEEE division/sqrt/log rather than
+// the SFU approximations, which keeps it within rounding of the reference's fp32 CPU result.
+#ifndef AZP_EVAL_COLLOID_CUH_
+#define AZP_EVAL_COLLOID_CUH_
+
+#include "eval_base.cuh"
+#include <cmath>
+
+namespace azp
+    {
+template<class S> class PairEvaluatorColloid : public PairEvaluatorBase<S>
+    {
+    public:
+    static constexpr int evaluator_id = 2;
+    struct alignas(4 * sizeof(S)) param_type : public PairParametersBase
+        {
+        S A;
+        S a_1;
+        S a_2;
+        S sigma_3;
+        };
+
+    enum Coupling
+        {
+        SolventSolvent = 0,
+        ColloidSolvent = 1,
+        ColloidColloid = 2
+        };
+
+    struct cache_type
+        {
+        S A;
+        S sigma_3;
+        S sigma_6;
+        S ai;
+        S aj;
+        S e_cut;
+        int coupling;
+        };
+
+    // ---- the three couplings; `force` selects whether force_divr is produced -------------
+    template<bool force> AZP_HD static S solventSolvent(const cache_type& c, S rsq, S& fdr)
+        {
+#ifdef __CUDA_ARCH__
+        const S r2inv = fast::rcp(rsq);
+#else
+        const S r2inv = S(1.0) / rsq;
+#endif
+        const S r6inv = r2inv * r2inv * r2inv;
+        const S c1 = c.A * c.sigma_6 / S(36.0);
+        if (force)
+            fdr = S(6.0) * c1 * r2inv * r6inv * (S(2.0) * c.sigma_6 * r6inv - S(1.0));
+        return c1 * r6inv * (c.sigma_6 * r6inv - S(1.0));
+        }
+
+    template<bool force> AZP_HD static S colloidSolvent(const cache_type& c, S rsq, S& fdr)
+        {
+        const S a = (c.ai > c.aj) ? c.ai : c.aj;
+        const S asq = a * a;
+        const S d = asq - rsq;
+        const S r4 = rsq * rsq;
+        const S d3 = d * d * d;
+        const S d6 = d3 * d3;
+#ifdef __CUDA_ARCH__
+        const S d3inv = fast::rcp(d3);
+        const S d6inv = d3inv * d3inv;
+        const S dinv = fast::rcp(d);
+#else
+        const S d3inv = S(1.0) / d3;
+        const S d6inv = S(1.0) / d6;
+        const S dinv = S(1.0) / d;
+#endif
+        const S fR = c.sigma_3 * c.A * a * asq * d3inv;
+        if (force)
+            {
+            fdr = S(4.0 / 15.0) * fR
+                  * (S(2.0) * (asq + rsq) * (asq * (S(5.0) * asq + S(22.0) * rsq) + S(5.0) * r4)
+                         * c.sigma_6 * d6inv
+                     - S(5.0))
+                  * dinv;
+            }
+        return S(2.0 / 9.0) * fR
+               * (S(1.0)
+                  - (asq * (asq * (asq / S(3.0) + S(3.0) * rsq) + S(4.2) * r4) + rsq * r4)
+                        * c.sigma_6 * d6inv);
+        }
+
+    AZP_HD static S inv7(S x)
+        {
+        const S xi = S(1.0) / x;
+        S g = xi * xi;
+        g *= g * g;
+        g *= xi;
+        return g;
+        }
+
+    template<bool force> AZP_HD static S colloidColloid(const cache_type& c, S rsq, S& fdr)
+        {
+        const S r = ::sqrt(rsq);
+        const S k0 = c.ai * c.aj, k1 = c.ai + c.aj, k2 = c.ai - c.aj;
+        const S k3 = k1 + r, k4 = k1 - r, k5 = k2 + r, k6 = k2 - r;
+        const S k7 = S(1.0) / (k3 * k4);
+        const S k8 = S(1.0) / (k5 * k6);
+        S g0 = inv7(k3), g1 = inv7(k4), g2 = inv7(k5), g3 = inv7(k6);
+        const S h0 = ((k3 + S(5.0) * k1) * k3 + S(30.0) * k0) * g0;
+        const S h1 = ((k4 + S(5.0) * k1) * k4 + S(30.0) * k0) * g1;
+        const S h2 = ((k5 + S(5.0) * k2) * k5 - S(30.0) * k0) * g2;
+        const S h3 = ((k6 + S(5.0) * k2) * k6 - S(30.0) * k0) * g3;
+        g0 *= S(42.0) * k0 / k3 + S(6.0) * k1 + k3;
+        g1 *= S(42.0) * k0 / k4 + S(6.0) * k1 + k4;
+        g2 *= S(-42.0) * k0 / k5 + S(6.0) * k2 + k5;
+        g3 *= S(-42.0) * k0 / k6 + S(6.0) * k2 + k6;
+        const S fR = c.A * c.sigma_6 / r / S(37800.0);
+        S eng = fR * (h0 - h1 - h2 + h3);
+        if (force)
+            {
+            const S dUR = eng / r + S(5.0) * fR * (g0 + g1 - g2 - g3);
+            const S dUA = -c.A / S(3.0) * r
+                          * ((S(2.0) * k0 * k7 + S(1.0)) * k7 + (S(2.0) * k0 * k8 - S(1.0)) * k8);
+            fdr = (dUR + dUA) / r;
+            }
+        eng += c.A / S(6.0) * (S(2.0) * k0 * (k7 + k8) - ::log(k8 / k7));
+        return eng;
+        }
+
+    AZP_HD static cache_type make_cache(const param_type& p, S rcutsq, bool energy_shift)
+        {
+        cache_type c;
+        c.A = p.A;
+        c.sigma_3 = p.sigma_3;
+        c.sigma_6 = p.sigma_3 * p.sigma_3;
+        c.ai = p.a_1;
+        c.aj = p.a_2;
+        if (p.a_1 == S(0) && p.a_2 == S(0))
+            c.coupling = SolventSolvent;
+        else if (p.a_1 != S(0) && p.a_2 != S(0))
+            c.coupling = ColloidColloid;
+        else
+            c.coupling = ColloidSolvent;
+        c.e_cut = S(0);
+        if (energy_shift && p.A != S(0))
+            {
+            S unused = S(0);
+            if (c.coupling == SolventSolvent)
+                c.e_cut = solventSolvent<false>(c, rcutsq, unused);
+            else if (c.coupling == ColloidColloid)
+                c.e_cut = colloidColloid<false>(c, rcutsq, unused);
+            else
+                c.e_cut = colloidSolvent<false>(c, rcutsq, unused);
+            }
+        return c;
+        }
+
+    AZP_D PairEvaluatorColloid(S _rsq, S _rcutsq, const cache_type& _c)
+        : PairEvaluatorBase<S>(_rsq, _rcutsq), c(_c)
+        {
+        }
+
+    AZP_D bool evalForceAndEnergy(S& force_divr, S& pair_eng, bool)
+        {
+        if (this->rsq < this->rcutsq && c.A != S(0))
+            {
+            S e;
+            if (c.coupling == SolventSolvent)
+                e = solventSolvent<true>(c, this->rsq, force_divr);
+            else if (c.coupling == ColloidSolvent)
+                e = colloidSolvent<true>(c, this->rsq, force_divr);
+            else
+                e = colloidColloid<true>(c, this->rsq, force_divr);
+            pair_eng = e - c.e_cut;
+            return true;
+            }
+        return false;
+        }
+
+    static const char* getName()
+        {
+        return "colloid";
+        }
+    // fields {A, a_1, a_2, sigma}
+    static void pack(const double* f, param_type* p)
+        {
+        p->A = S(f[0]);
+        p->a_1 = S(f[1]);
+        p->a_2 = S(f[2]);
+        const S sigma = S(f[3]);
+        p->sigma_3 = sigma * sigma * sigma;
+        }
+    static void unpack(const param_type* p, double* f)
+        {
+        f[0] = double(p->A);
+        f[1] = double(p->a_1);
+        f[2] = double(p->a_2);
+        f[3] = double(std::cbrt(p->sigma_3));
+        }
+    static constexpr int num_fields = 4;
+
+    private:
+    const cache_type& c;
+    };
+    } // namespace azp
+#endif

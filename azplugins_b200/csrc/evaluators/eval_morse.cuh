@@ -1,0 +1,194 @@
+// eval_morse.cuh -- two-patch Morse: U = U_Morse(r) Omega(rhat.n_i) Omega(rhat.n_j), forces and
+// torques. Behaviour: reference src/AnisoPairEvaluatorTwoPatchMorse.h:32-69 (param_type),
+// :127-216 (evaluate); contract of src/AnisoPairEvaluator.h:97-215 (no charge/shape/tags,
+// implementsEnergyShift).
+//
+// The patch director n = rotate(q, (1,0,0)) is written out for the unit x axis:
+//   n = (s^2 + x^2 - y^2 - z^2, 2 (x y + s z), 2 (x z - s y))      q = (s, x, y, z)
+// n_i depends only on the row, so the kernel's compiler hoists it out of the neighbour loop.
+// U_Morse(r_cut) for the energy shift is hoisted per type pair.
+#ifndef AZP_EVAL_MORSE_CUH_
+#define AZP_EVAL_MORSE_CUH_
+
+#include "eval_base.cuh"
+
+namespace azp
+    {
+struct AnisoShapeParametersEmpty
+    {
+    AZP_D void load_shared(char*&, unsigned int&) { }
+    AZP_HD void allocate_shared(char*&, unsigned int&) const { }
+    void set_memory_hint() const { }
+    };
+
+template<class S> AZP_D Vec3<S> patch_director(const Vec4<S>& q)
+    {
+    // Scalar4 (x,y,z,w) carries the quaternion (s, v.x, v.y, v.z)
+    const S s = q.x, a = q.y, b = q.z, c = q.w;
+    Vec3<S> n;
+    n.x = (s * s - (a * a + b * b + c * c)) + S(2) * a * a;
+    n.y = S(2) * (s * c) + S(2) * a * b;
+    n.z = S(2) * a * c - S(2) * (s * b);
+    return n;
+    }
+
+template<class S> class AnisoPairEvaluatorTwoPatchMorse
+    {
+    public:
+    static constexpr int evaluator_id = 5;
+    // 5 Scalars + bool, no alignment attribute: 24 B (fp32) / 48 B (fp64) like the reference
+    struct param_type : public PairParametersBase
+        {
+        S M_d;
+        S M_rinv;
+        S r_eq;
+        S omega;
+        S alpha;
+        bool repulsion;
+        };
+    typedef AnisoShapeParametersEmpty shape_type;
+
+    struct cache_type
+        {
+        S M_d;
+        S M_rinv;
+        S r_eq;
+        S omega;
+        S alpha;
+        S U_cut; // U_Morse(r_cut) when shifting, else 0
+        int repulsion;
+        };
+
+    AZP_HD static cache_type make_cache(const param_type& p, S rcutsq, bool energy_shift)
+        {
+        cache_type c;
+        c.M_d = p.M_d;
+        c.M_rinv = p.M_rinv;
+        c.r_eq = p.r_eq;
+        c.omega = p.omega;
+        c.alpha = p.alpha;
+        c.repulsion = p.repulsion ? 1 : 0;
+        c.U_cut = S(0);
+        if (energy_shift)
+            {
+            const S rcut = ::sqrt(rcutsq);
+            const S e = ::exp(-(rcut - p.r_eq) * p.M_rinv);
+            const S om = S(1.0) - e;
+            c.U_cut = p.M_d * (om * om - S(1.0));
+            }
+        return c;
+        }
+
+    AZP_D AnisoPairEvaluatorTwoPatchMorse(const Vec3<S>& _dr,
+                                          const Vec4<S>& _quat_i,
+                                          const Vec4<S>& _quat_j,
+                                          S _rcutsq,
+                                          const cache_type& _c)
+        : dr(_dr), rcutsq(_rcutsq), quat_i(_quat_i), quat_j(_quat_j), c(_c)
+        {
+        }
+
+    AZP_HD static bool needsCharge()
+        {
+        return false;
+        }
+    AZP_D void setCharge(S, S) { }
+    AZP_HD static bool needsShape()
+        {
+        return false;
+        }
+    AZP_D void setShape(const shape_type*, const shape_type*) { }
+    AZP_HD static bool needsTags()
+        {
+        return false;
+        }
+    AZP_D void setTags(unsigned int, unsigned int) { }
+    AZP_HD static constexpr bool implementsEnergyShift()
+        {
+        return true;
+        }
+
+    AZP_D bool evaluate(Vec3<S>& force, S& pair_eng, bool, Vec3<S>& torque_i, Vec3<S>& torque_j)
+        {
+        const S rsq = dr.x * dr.x + dr.y * dr.y + dr.z * dr.z;
+        if (rsq > rcutsq) // the reference rejects only strictly-greater (:135)
+            return false;
+        const S rinv = fast::rsqrt(rsq);
+        const S r = rsq * rinv;
+        const Vec3<S> u {dr.x * rinv, dr.y * rinv, dr.z * rinv};
+        const Vec3<S> ni = patch_director(quat_i);
+        const Vec3<S> nj = patch_director(quat_j);
+
+        S UM = -c.M_d;
+        S dUM = S(0);
+        if (r > c.r_eq || c.repulsion)
+            {
+            const S me = fast::exp(-(r - c.r_eq) * c.M_rinv);
+            const S om = S(1.0) - me;
+            UM = c.M_d * (om * om - S(1.0));
+            dUM = S(2.0) * c.M_d * c.M_rinv * me * om;
+            }
+        const S gi = u.x * ni.x + u.y * ni.y + u.z * ni.z;
+        const S gie = fast::exp(-c.omega * (gi * gi - c.alpha));
+        const S Oi = fast::rcp(S(1.0) + gie);
+        const S gj = u.x * nj.x + u.y * nj.y + u.z * nj.z;
+        const S gje = fast::exp(-c.omega * (gj * gj - c.alpha));
+        const S Oj = fast::rcp(S(1.0) + gje);
+
+        const S OiOj = Oi * Oj;
+        const S dU_dr = dUM * OiOj;
+        const S dU_dgi = (S(2.0) * c.omega * gi * gie * Oi * Oi) * UM * Oj;
+        const S dU_dgj = (S(2.0) * c.omega * gj * gje * Oj * Oj) * UM * Oi;
+
+        // u x n and the in-plane director  n_perp = -u x (u x n) = n - (u.n) u
+        const Vec3<S> ci {u.y * ni.z - u.z * ni.y, u.z * ni.x - u.x * ni.z, u.x * ni.y - u.y * ni.x};
+        const Vec3<S> cj {u.y * nj.z - u.z * nj.y, u.z * nj.x - u.x * nj.z, u.x * nj.y - u.y * nj.x};
+        const Vec3<S> pi {ci.y * u.z - ci.z * u.y, ci.z * u.x - ci.x * u.z, ci.x * u.y - ci.y * u.x};
+        const Vec3<S> pj {cj.y * u.z - cj.z * u.y, cj.z * u.x - cj.x * u.z, cj.x * u.y - cj.y * u.x};
+
+        force.x = -dU_dr * u.x - rinv * (dU_dgi * pi.x + dU_dgj * pj.x);
+        force.y = -dU_dr * u.y - rinv * (dU_dgi * pi.y + dU_dgj * pj.y);
+        force.z = -dU_dr * u.z - rinv * (dU_dgi * pi.z + dU_dgj * pj.z);
+        torque_i = Vec3<S> {dU_dgi * ci.x, dU_dgi * ci.y, dU_dgi * ci.z};
+        torque_j = Vec3<S> {dU_dgj * cj.x, dU_dgj * cj.y, dU_dgj * cj.z};
+        pair_eng = (UM - c.U_cut) * OiOj;
+        return true;
+        }
+
+    static const char* getName()
+        {
+        return "TwoPatchMorse";
+        }
+    static const char* getShapeParamName()
+        {
+        return "";
+        }
+    // fields {M_d, M_r, r_eq, omega, alpha, repulsion}
+    static void pack(const double* f, param_type* p)
+        {
+        p->M_d = S(f[0]);
+        p->M_rinv = S(1.0) / S(f[1]);
+        p->r_eq = S(f[2]);
+        p->omega = S(f[3]);
+        p->alpha = S(f[4]);
+        p->repulsion = (f[5] != 0.0);
+        }
+    static void unpack(const param_type* p, double* f)
+        {
+        f[0] = double(p->M_d);
+        f[1] = double(S(1.0) / p->M_rinv);
+        f[2] = double(p->r_eq);
+        f[3] = double(p->omega);
+        f[4] = double(p->alpha);
+        f[5] = p->repulsion ? 1.0 : 0.0;
+        }
+    static constexpr int num_fields = 6;
+
+    private:
+    Vec3<S> dr;
+    S rcutsq;
+    Vec4<S> quat_i, quat_j;
+    const cache_type& c;
+    };
+    } // namespace azp
+#endif

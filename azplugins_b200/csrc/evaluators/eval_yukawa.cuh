@@ -1,0 +1,88 @@
+// eval_yukawa.cuh -- expanded (shifted-origin) Yukawa: U = eps exp(-kappa (r - delta)) / (r - delta).
+// Behaviour: reference src/PairEvaluatorExpandedYukawa.h:23-53 (param_type), :92-113.
+#ifndef AZP_EVAL_YUKAWA_CUH_
+#define AZP_EVAL_YUKAWA_CUH_
+
+#include "eval_base.cuh"
+
+namespace azp
+    {
+template<class S> class PairEvaluatorExpandedYukawa : public PairEvaluatorBase<S>
+    {
+    public:
+    static constexpr int evaluator_id = 1;
+    struct alignas(4 * sizeof(S)) param_type : public PairParametersBase
+        {
+        S epsilon;
+        S kappa;
+        S delta;
+        };
+
+    struct cache_type
+        {
+        S epsilon;
+        S kappa;
+        S delta;
+        S e_cut; // eps exp(-kappa (r_cut - delta)) / (r_cut - delta) when shifting, else 0
+        };
+
+    AZP_HD static cache_type make_cache(const param_type& p, S rcutsq, bool energy_shift)
+        {
+        cache_type c;
+        c.epsilon = p.epsilon;
+        c.kappa = p.kappa;
+        c.delta = p.delta;
+        c.e_cut = S(0);
+        if (energy_shift)
+            {
+            const S rcut = ::sqrt(rcutsq);
+            const S rcd = rcut - p.delta;
+            c.e_cut = p.epsilon * ::exp(-p.kappa * rcd) / rcd;
+            }
+        return c;
+        }
+
+    AZP_D PairEvaluatorExpandedYukawa(S _rsq, S _rcutsq, const cache_type& _c)
+        : PairEvaluatorBase<S>(_rsq, _rcutsq), c(_c)
+        {
+        }
+
+    AZP_D bool evalForceAndEnergy(S& force_divr, S& pair_eng, bool)
+        {
+        if (this->rsq < this->rcutsq && c.epsilon != S(0))
+            {
+            const S rinv = fast::rsqrt(this->rsq);
+            const S r = this->rsq * rinv;
+            const S rd = r - c.delta;
+            const S rdinv = fast::rcp(rd);
+            const S e = c.epsilon * fast::exp(-c.kappa * rd) * rdinv;
+            force_divr = e * (c.kappa + rdinv) * rinv;
+            pair_eng = e - c.e_cut;
+            return true;
+            }
+        return false;
+        }
+
+    static const char* getName()
+        {
+        return "ExpandedYukawa";
+        }
+    static void pack(const double* f, param_type* p)
+        {
+        p->epsilon = S(f[0]);
+        p->kappa = S(f[1]);
+        p->delta = S(f[2]);
+        }
+    static void unpack(const param_type* p, double* f)
+        {
+        f[0] = double(p->epsilon);
+        f[1] = double(p->kappa);
+        f[2] = double(p->delta);
+        }
+    static constexpr int num_fields = 3;
+
+    private:
+    const cache_type& c;
+    };
+    } // namespace azp
+#endif

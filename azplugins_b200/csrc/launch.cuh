@@ -1,0 +1,259 @@
+// launch.cuh -- host launch layer: argument conversion, launch-parameter choice, dispatch over
+// the (xplor, virial, single-type) instantiations. This is the B200 counterpart of the
+// shift_mode x compute_virial x threads_per_particle switch inside HOOMD's
+// gpu_compute_pair_forces<E> driver; threads_per_particle is
+// a runtime argument of the kernels here, so only 8 (iso) / 4 (dpd, aniso) variants are compiled.
+#ifndef AZP_LAUNCH_CUH_
+#define AZP_LAUNCH_CUH_
+
+#include "../../include/azp_b200.h"
+#include "pair_kernels.cuh"
+
+namespace azp
+    {
+template<class S> inline BoxDim<S> convert_box(const azp_box& b)
+    {
+    BoxDim<S> o;
+    for (int d = 0; d < 3; ++d)
+        {
+        o.L[d] = S(b.L[d]);
+        o.Linv[d] = S(1.0) / o.L[d];
+        o.periodic[d] = b.periodic[d];
+        }
+    o.xy = S(b.tilt[0]);
+    o.xz = S(b.tilt[1]);
+    o.yz = S(b.tilt[2]);
+    const bool tilted = (o.xy != S(0)) || (o.xz != S(0)) || (o.yz != S(0));
+    const bool periodic3 = b.periodic[0] && b.periodic[1] && b.periodic[2];
+    o.flags = (!tilted && periodic3) ? 2 : (tilted ? 1 : 0);
+    return o;
+    }
+
+template<class S> inline KernelArgs<S> convert_args(const azp_pair_args& a)
+    {
+    KernelArgs<S> k;
+    k.force = static_cast<S*>(a.d_force);
+    k.virial = static_cast<S*>(a.d_virial);
+    k.torque = static_cast<S*>(a.d_torque);
+    k.virial_pitch = (size_t)a.virial_pitch;
+    k.pos = static_cast<const S*>(a.d_pos);
+    k.vel = static_cast<const S*>(a.d_vel);
+    k.orientation = static_cast<const S*>(a.d_orientation);
+    k.tag = a.d_tag;
+    k.n_neigh = a.d_n_neigh;
+    k.nlist = a.d_nlist;
+    k.head_list = a.d_head_list;
+    k.rcutsq = static_cast<const S*>(a.d_rcutsq);
+    k.ronsq = static_cast<const S*>(a.d_ronsq);
+    k.row_ids = a.d_row_ids;
+    k.box = convert_box<S>(a.box);
+    k.N = a.N;
+    k.ntypes = a.ntypes;
+    k.shift_mode = a.shift_mode;
+    k.row_offset = a.row_offset;
+    k.n_row_ids = a.n_row_ids;
+    k.seed = a.seed & 0xffffu;
+    k.timestep = (unsigned int)(a.timestep & 0xffffffffull);
+    k.deltaT = S(a.deltaT);
+    k.T = S(a.T);
+    return k;
+    }
+
+struct LaunchShape
+    {
+    unsigned int block;
+    unsigned int tpp_log2;
+    unsigned int grid;
+    };
+
+inline bool is_pow2(unsigned int x)
+    {
+    return x && !(x & (x - 1));
+    }
+
+// Launch parameters: honour the caller's (block_size, threads_per_particle) -- HOOMD's autotuner
+// dimensions -- or choose from the mean row capacity: about 12-16 neighbours per lane keeps the
+// tail waste of a row under 5 % while leaving enough rows per warp for coalesced outputs.
+inline cudaError_t choose_shape(const azp_pair_args& a, LaunchShape& s)
+    {
+    unsigned int block = a.block_size ? a.block_size : 128u;
+    if (block % 32u != 0 || block > kMaxBlock)
+        return cudaErrorInvalidValue;
+    unsigned int tpp = a.threads_per_particle;
+    if (tpp == 0)
+        {
+        const unsigned int rows = a.N ? a.N : 1u;
+        const double mean_cap = a.size_neigh_list ? double(a.size_neigh_list) / rows : 64.0;
+        tpp = 1;
+        while (tpp < 32u && mean_cap / tpp > 18.0)
+            tpp <<= 1;
+        }
+    if (!is_pow2(tpp) || tpp > 32u)
+        return cudaErrorInvalidValue;
+    unsigned int lg = 0;
+    while ((1u << lg) < tpp)
+        ++lg;
+    const unsigned long long nslots = a.d_row_ids ? a.n_row_ids : a.N;
+    const unsigned long long threads = nslots * tpp;
+    const unsigned long long grid = (threads + block - 1) / block;
+    if (grid > 0x7fffffffull)
+        return cudaErrorInvalidValue;
+    s.block = block;
+    s.tpp_log2 = lg;
+    s.grid = (unsigned int)grid;
+    return cudaSuccess;
+    }
+
+inline cudaError_t check_common(const azp_pair_args* a, const void* d_params)
+    {
+    if (!a || !d_params)
+        return cudaErrorInvalidValue;
+    if (a->ntypes == 0)
+        return cudaErrorInvalidValue;
+    if (a->N == 0 || (a->d_row_ids && a->n_row_ids == 0))
+        return cudaSuccess; // nothing to do; caught by the callers before launching
+    if (!a->d_force || !a->d_pos || !a->d_n_neigh || !a->d_nlist || !a->d_head_list || !a->d_rcutsq)
+        return cudaErrorInvalidValue;
+    if (a->compute_virial > 1 || (a->compute_virial && !a->d_virial))
+        return cudaErrorInvalidValue;
+    return cudaSuccess;
+    }
+
+inline bool nothing_to_do(const azp_pair_args* a)
+    {
+    return a->N == 0 || (a->d_row_ids && a->n_row_ids == 0);
+    }
+
+template<class K> inline cudaError_t ensure_smem(K kernel, size_t bytes)
+    {
+    if (bytes > 227u * 1024u)
+        return cudaErrorInvalidValue; // type-pair table does not fit in shared memory
+    if (bytes > 48u * 1024u)
+        return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    return cudaSuccess;
+    }
+
+template<class E, class S, bool XPLOR, bool VIRIAL, bool NT1>
+inline cudaError_t launch_pair_variant(const KernelArgs<S>& k, const void* d_params, const LaunchShape& s, cudaStream_t stream)
+    {
+    typedef typename E::cache_type Cache;
+    const size_t ntp = NT1 ? 1 : size_t(k.ntypes) * k.ntypes;
+    const size_t smem = ntp * sizeof(Cache) + (ntp + 1) * sizeof(S) + (XPLOR ? ntp * sizeof(XplorEntry<S>) : 0) + 16;
+    auto kernel = pair_force_kernel<E, S, XPLOR, VIRIAL, NT1>;
+    cudaError_t err = ensure_smem(kernel, smem);
+    if (err != cudaSuccess)
+        return err;
+    kernel<<<s.grid, s.block, smem, stream>>>(k, static_cast<const typename E::param_type*>(d_params), s.tpp_log2);
+    return cudaGetLastError();
+    }
+
+template<class E, class S> cudaError_t launch_pair(const azp_pair_args* a, const void* d_params, cudaStream_t stream)
+    {
+    cudaError_t err = check_common(a, d_params);
+    if (err != cudaSuccess)
+        return err;
+    if (a->shift_mode > 2 || (a->shift_mode == 2 && !a->d_ronsq))
+        return cudaErrorInvalidValue;
+    if (nothing_to_do(a))
+        return cudaSuccess;
+    LaunchShape s;
+    err = choose_shape(*a, s);
+    if (err != cudaSuccess)
+        return err;
+    const KernelArgs<S> k = convert_args<S>(*a);
+    const bool xplor = a->shift_mode == 2, vir = a->compute_virial != 0, nt1 = a->ntypes == 1;
+#define AZP_CASE(X, V, T)           \
+    if (xplor == X && vir == V && nt1 == T) \
+        return launch_pair_variant<E, S, X, V, T>(k, d_params, s, stream);
+    AZP_CASE(false, false, false)
+    AZP_CASE(false, false, true)
+    AZP_CASE(false, true, false)
+    AZP_CASE(false, true, true)
+    AZP_CASE(true, false, false)
+    AZP_CASE(true, false, true)
+    AZP_CASE(true, true, false)
+    AZP_CASE(true, true, true)
+#undef AZP_CASE
+    return cudaErrorInvalidValue;
+    }
+
+template<class E, class S, bool VIRIAL, bool NT1>
+inline cudaError_t launch_dpd_variant(const KernelArgs<S>& k, const void* d_params, const LaunchShape& s, cudaStream_t stream)
+    {
+    typedef typename E::cache_type Cache;
+    const size_t ntp = NT1 ? 1 : size_t(k.ntypes) * k.ntypes;
+    const size_t smem = ntp * sizeof(Cache) + (ntp + 1) * sizeof(S) + 16;
+    auto kernel = dpd_force_kernel<E, S, VIRIAL, NT1>;
+    cudaError_t err = ensure_smem(kernel, smem);
+    if (err != cudaSuccess)
+        return err;
+    kernel<<<s.grid, s.block, smem, stream>>>(k, static_cast<const typename E::param_type*>(d_params), s.tpp_log2);
+    return cudaGetLastError();
+    }
+
+template<class E, class S> cudaError_t launch_dpd(const azp_pair_args* a, const void* d_params, cudaStream_t stream)
+    {
+    cudaError_t err = check_common(a, d_params);
+    if (err != cudaSuccess)
+        return err;
+    if (nothing_to_do(a))
+        return cudaSuccess;
+    if (!a->d_vel || !a->d_tag)
+        return cudaErrorInvalidValue;
+    LaunchShape s;
+    err = choose_shape(*a, s);
+    if (err != cudaSuccess)
+        return err;
+    const KernelArgs<S> k = convert_args<S>(*a);
+    const bool vir = a->compute_virial != 0, nt1 = a->ntypes == 1;
+    if (vir && nt1)
+        return launch_dpd_variant<E, S, true, true>(k, d_params, s, stream);
+    if (vir)
+        return launch_dpd_variant<E, S, true, false>(k, d_params, s, stream);
+    if (nt1)
+        return launch_dpd_variant<E, S, false, true>(k, d_params, s, stream);
+    return launch_dpd_variant<E, S, false, false>(k, d_params, s, stream);
+    }
+
+template<class E, class S, bool VIRIAL, bool NT1>
+inline cudaError_t launch_aniso_variant(const KernelArgs<S>& k, const void* d_params, const LaunchShape& s, cudaStream_t stream)
+    {
+    typedef typename E::cache_type Cache;
+    const size_t ntp = NT1 ? 1 : size_t(k.ntypes) * k.ntypes;
+    const size_t smem = ntp * sizeof(Cache) + (ntp + 1) * sizeof(S) + 16;
+    auto kernel = aniso_force_kernel<E, S, VIRIAL, NT1>;
+    cudaError_t err = ensure_smem(kernel, smem);
+    if (err != cudaSuccess)
+        return err;
+    kernel<<<s.grid, s.block, smem, stream>>>(k, static_cast<const typename E::param_type*>(d_params), s.tpp_log2);
+    return cudaGetLastError();
+    }
+
+template<class E, class S> cudaError_t launch_aniso(const azp_pair_args* a, const void* d_params, cudaStream_t stream)
+    {
+    cudaError_t err = check_common(a, d_params);
+    if (err != cudaSuccess)
+        return err;
+    if (a->shift_mode > 1)
+        return cudaErrorInvalidValue; // AnisotropicPair accepts none / shift only
+    if (nothing_to_do(a))
+        return cudaSuccess;
+    if (!a->d_orientation || !a->d_torque)
+        return cudaErrorInvalidValue;
+    LaunchShape s;
+    err = choose_shape(*a, s);
+    if (err != cudaSuccess)
+        return err;
+    const KernelArgs<S> k = convert_args<S>(*a);
+    const bool vir = a->compute_virial != 0, nt1 = a->ntypes == 1;
+    if (vir && nt1)
+        return launch_aniso_variant<E, S, true, true>(k, d_params, s, stream);
+    if (vir)
+        return launch_aniso_variant<E, S, true, false>(k, d_params, s, stream);
+    if (nt1)
+        return launch_aniso_variant<E, S, false, true>(k, d_params, s, stream);
+    return launch_aniso_variant<E, S, false, false>(k, d_params, s, stream);
+    }
+    } // namespace azp
+
+#endif

@@ -1,0 +1,174 @@
+"""Neighbour lists in HOOMD's ``NeighborListGPU`` layout.
+
+``Cell`` mirrors ``hoomd.md.nlist.Cell(buffer, ...)`` (the list every reference test uses,
+reference src/pytest/test_pair.py:337): a full list with r_list = r_cut(type pair) + buffer,
+built on the GPU by ``azp_nlist_*`` (csrc/nlist_kernels.cu) and rebuilt when any particle has
+moved more than buffer/2 since the last build. ``NeighborList.from_arrays`` wraps arrays built
+elsewhere (e.g. by HOOMD itself) without copying semantics changes.
+"""
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+class NeighborList:
+    """Holder of ``n_neigh`` (u32[N]), ``nlist`` (u32[size]) and ``head_list`` (u64[N])."""
+
+    storage_mode = "full"
+
+    def __init__(self, buffer=0.4, exclusions=(), rebuild_check_delay=1, check_dist=True,
+                 default_r_cut=0.0):
+        self.buffer = float(buffer)
+        self.exclusions = tuple(exclusions)
+        self.rebuild_check_delay = int(rebuild_check_delay)
+        self.check_dist = bool(check_dist)
+        self.default_r_cut = float(default_r_cut)
+        self._consumers = []
+        self.n_neigh = None
+        self.nlist = None
+        self.head_list = None
+        self.size = 0
+        self.num_builds = 0
+        self._pos_at_build = None
+        self._external = False
+
+    # ---- consumers: the list must cover the largest r_cut of every attached potential ------
+    def _add_consumer(self, force):
+        if force not in self._consumers:
+            self._consumers.append(force)
+            self.n_neigh = None  # r_cut may have grown
+
+    def r_cut_matrix(self, state):
+        nt = state.ntypes
+        rc = np.full((nt, nt), self.default_r_cut, dtype=np.float64)
+        for f in self._consumers:
+            rc = np.maximum(rc, f._r_cut_matrix(state))
+        return rc
+
+    @classmethod
+    def from_arrays(cls, n_neigh, nlist, head_list, device="cuda:0", buffer=0.0):
+        """Adopt an existing HOOMD-layout list (numpy or torch arrays)."""
+        self = cls(buffer=buffer)
+        dev = torch.device(device)
+
+        def conv(a, np_dtype, view):
+            if isinstance(a, torch.Tensor):
+                return a.to(dev).contiguous()
+            return torch.from_numpy(np.ascontiguousarray(a, dtype=np_dtype).view(view)).to(dev)
+
+        self.n_neigh = conv(n_neigh, np.uint32, np.int32)
+        self.nlist = conv(nlist, np.uint32, np.int32)
+        self.head_list = conv(head_list, np.uint64, np.int64)
+        self.size = int(self.nlist.numel())
+        self._external = True
+        return self
+
+    def compute(self, state):
+        if self._external:
+            return False
+        if self.n_neigh is None or self._needs_rebuild(state):
+            self.build(state)
+            return True
+        return False
+
+    def build(self, state):
+        raise NotImplementedError
+
+    def _needs_rebuild(self, state):
+        if not self.check_dist or self._pos_at_build is None:
+            return self._pos_at_build is None
+        if self._pos_at_build.shape != state.pos.shape:
+            return True
+        d = state.pos[:, :3] - self._pos_at_build[:, :3]
+        L = torch.tensor(state.box.L, dtype=d.dtype, device=d.device)
+        per = torch.tensor([float(p) for p in state.box.periodic], dtype=d.dtype, device=d.device)
+        d = d - per * L * torch.round(d / L)
+        return bool((d * d).sum(dim=1).max() > (0.5 * self.buffer) ** 2)
+
+    def to_numpy(self):
+        return (self.n_neigh.cpu().numpy().view(np.uint32),
+                self.nlist.cpu().numpy().view(np.uint32),
+                self.head_list.cpu().numpy().view(np.uint64))
+
+
+class Cell(NeighborList):
+    """Cell-list neighbour search on the GPU; ctor mirrors ``hoomd.md.nlist.Cell``."""
+
+    def __init__(self, buffer, exclusions=("bond",), rebuild_check_delay=1, check_dist=True,
+                 deterministic=False, mesh=None, default_r_cut=0.0, row_align=8):
+        super().__init__(buffer, exclusions, rebuild_check_delay, check_dist, default_r_cut)
+        self.deterministic = deterministic
+        self.row_align = int(row_align)
+
+    def build(self, state):
+        if not state.pos.is_cuda:
+            raise _lib.AzpError("nlist.Cell builds on the GPU only (no CPU fallback)")
+        bits = 8 * state.dtype.itemsize
+        sfx = "_f%d" % bits
+        nt = state.ntypes
+        r_list = self.r_cut_matrix(state) + self.buffer
+        r_list[self.r_cut_matrix(state) <= 0] = 0.0
+        r_max = float(r_list.max())
+        if not r_max > 0:
+            raise ValueError("neighbour list has no positive r_cut")
+        for d in range(3):
+            if state.box.periodic[d] and state.box.L[d] < 2.0 * r_max:
+                raise ValueError("box too small for r_cut + buffer (minimum image)")
+        dev = state.device
+        n_total = state.pos.shape[0]
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        with torch.cuda.device(dev):
+            rl = r_list.astype(state.dtype)
+            rlsq = torch.from_numpy((rl * rl).reshape(-1).copy()).to(dev)
+            a = _lib.AzpNlistArgs()
+            a.d_pos = state.pos.data_ptr()
+            a.N = n_total
+            a.ntypes = nt
+            a.box = state.box.to_c()
+            a.d_rlistsq = rlsq.data_ptr()
+            a.r_list_max = r_max
+            dim = (ctypes.c_uint32 * 3)()
+            _lib.check(_lib.lib.azp_nlist_cell_dim(ctypes.byref(a.box), r_max, dim), "cell_dim")
+            ncells = int(dim[0]) * int(dim[1]) * int(dim[2])
+            for d in range(3):
+                a.cell_dim[d] = dim[d]
+            cell_of = torch.empty(n_total, dtype=torch.int32, device=dev)
+            cell_start = torch.empty(ncells + 1, dtype=torch.int32, device=dev)
+            cell_order = torch.empty(n_total, dtype=torch.int32, device=dev)
+            n_neigh = torch.empty(n_total, dtype=torch.int32, device=dev)
+            a.d_cell_of = cell_of.data_ptr()
+            a.d_cell_start = cell_start.data_ptr()
+            a.d_cell_order = cell_order.data_ptr()
+            a.d_n_neigh = n_neigh.data_ptr()
+            _lib.check(getattr(_lib.lib, "azp_nlist_bin" + sfx)(ctypes.byref(a), stream), "nlist bin")
+            _lib.check(getattr(_lib.lib, "azp_nlist_count" + sfx)(ctypes.byref(a), stream), "nlist count")
+            # head_list = prefix sum of Nmax[type] (HOOMD's row capacity rule)
+            typeid = particle_typeid(state.pos)
+            cap = torch.zeros(n_total, dtype=torch.int64, device=dev)
+            for t in range(nt):
+                sel = typeid == t
+                if bool(sel.any()):
+                    m = int(n_neigh[sel].max())
+                    m = (m + self.row_align - 1) // self.row_align * self.row_align
+                    cap[sel] = m
+            head = torch.cumsum(cap, 0) - cap
+            size = int(cap.sum())
+            nlist = torch.zeros(max(size, 1), dtype=torch.int32, device=dev)
+            a.d_head_list = head.data_ptr()
+            a.d_nlist = nlist.data_ptr()
+            _lib.check(getattr(_lib.lib, "azp_nlist_fill" + sfx)(ctypes.byref(a), stream), "nlist fill")
+        # rows of ghosts are built too but only the first N rows are consumed
+        self.n_neigh, self.nlist, self.head_list, self.size = n_neigh, nlist, head, size
+        self._pos_at_build = state.pos.clone()
+        self.num_builds += 1
+
+
+def particle_typeid(pos):
+    """Type ids bit-cast in pos[:, 3] (torch tensor, fp32 or fp64)."""
+    if pos.dtype == torch.float32:
+        return pos[:, 3].contiguous().view(torch.int32).to(torch.int64)
+    return pos[:, 3].contiguous().view(torch.int64) & 0xFFFFFFFF

@@ -1,0 +1,353 @@
+"""Pair potentials -- the ``hoomd.azplugins.pair`` API surface on the B200 kernels.
+
+Same class names, constructor arguments, ``params`` keys, ``r_cut`` / ``r_on`` / ``mode`` / ``kT``
+semantics and C++ class-name mapping as reference ``src/pair.py`` (Colloid :14-118,
+DPDGeneralWeight :121-239, ExpandedYukawa :242-297, Hertz :300-351, PerturbedLennardJones
+:354-426, TwoPatchMorse :429-525), and the ``Force`` read-outs HOOMD exposes (``forces``,
+``energies``, ``energy``, ``torques``, ``virials``). HOOMD itself is not required: a potential
+attaches to an ``azplugins_b200.State`` and computes through the C ABI in
+``include/azp_b200.h``. INTEGRATION.md shows how the same kernels slot under a real HOOMD build.
+
+There is no CPU implementation behind these classes: ``hoomd.device.CPU``-style execution is
+out of scope and attaching to a non-CUDA state raises.
+"""
+
+import numpy as np
+import torch
+
+from . import _lib, kernels
+from .nlist import NeighborList
+
+
+class _TypePairDict:
+    """``TypeParameterDict(..., len_keys=2)`` work-alike: values keyed by unordered type pairs."""
+
+    def __init__(self, schema=None, default=None):
+        self._schema = schema  # ordered {key: python type} or None for scalar entries
+        self._default = default
+        self._data = {}
+
+    @staticmethod
+    def _key(key):
+        if not (isinstance(key, tuple) and len(key) == 2):
+            raise KeyError("type-pair keys are 2-tuples of type names, got %r" % (key,))
+        a, b = key
+        return (a, b) if a <= b else (b, a)
+
+    def _validate(self, value):
+        if self._schema is None:
+            return None if value is None else float(value)
+        if not isinstance(value, dict):
+            raise TypeError("parameters must be given as a dict")
+        missing = [k for k in self._schema if k not in value]
+        extra = [k for k in value if k not in self._schema]
+        if missing or extra:
+            raise KeyError("parameter dict mismatch: missing %s, unexpected %s" % (missing, extra))
+        out = {}
+        for k, typ in self._schema.items():
+            out[k] = bool(value[k]) if typ is bool else float(value[k])
+        return out
+
+    def __setitem__(self, key, value):
+        if isinstance(key, tuple) and len(key) == 2 and any(isinstance(k, (list, tuple)) for k in key):
+            # HOOMD allows (["A","B"], ["A","B"]) style multi-keys
+            la = key[0] if isinstance(key[0], (list, tuple)) else [key[0]]
+            lb = key[1] if isinstance(key[1], (list, tuple)) else [key[1]]
+            for a in la:
+                for b in lb:
+                    self[(a, b)] = value
+            return
+        self._data[self._key(key)] = self._validate(value)
+
+    def __getitem__(self, key):
+        k = self._key(key)
+        if k in self._data:
+            v = self._data[k]
+            return dict(v) if isinstance(v, dict) else v
+        if self._default is not None:
+            return self._default
+        raise KeyError("no value set for type pair %r" % (key,))
+
+    def __contains__(self, key):
+        return self._key(key) in self._data
+
+    def keys(self):
+        return self._data.keys()
+
+    @property
+    def default(self):
+        return self._default
+
+    @default.setter
+    def default(self, v):
+        self._default = self._validate(v)
+
+
+class Pair:
+    """Base of the isotropic pair potentials (``hoomd.md.pair.Pair`` work-alike, Appendix A.9)."""
+
+    _cpp_class_name = None
+    _evaluator = None
+    _family = _lib.FAMILY_PAIR
+    _accepted_modes = ("none", "shift", "xplor")
+    _param_schema = {}
+    is_anisotropic = False
+
+    def __init__(self, nlist, default_r_cut=None, default_r_on=0.0, mode="none"):
+        if not isinstance(nlist, NeighborList):
+            raise TypeError("nlist must be an azplugins_b200.nlist.NeighborList")
+        self.nlist = nlist
+        self.params = _TypePairDict(schema=dict(self._param_schema))
+        self.r_cut = _TypePairDict(default=None if default_r_cut is None else float(default_r_cut))
+        self.r_on = _TypePairDict(default=float(default_r_on))
+        self.mode = mode
+        self._state = None
+        self._launch_shape = (0, 0)  # (block_size, threads_per_particle); 0 = library default
+        nlist._add_consumer(self)
+
+    # ---- configuration -------------------------------------------------------------------
+    @property
+    def mode(self):
+        return self._mode
+
+    @mode.setter
+    def mode(self, value):
+        if value not in self._accepted_modes:
+            raise ValueError("mode must be one of %s" % (self._accepted_modes,))
+        self._mode = value
+
+    @property
+    def cpp_class_name(self):
+        """Name of the C++ class HOOMD would instantiate on a GPU device (``+"GPU"``)."""
+        return self._cpp_class_name + "GPU"
+
+    @property
+    def kernel_parameters(self):
+        """(block_size, threads_per_particle) -- HOOMD's Autotuner<2> dimensions."""
+        return self._launch_shape
+
+    @kernel_parameters.setter
+    def kernel_parameters(self, value):
+        self._launch_shape = (int(value[0]), int(value[1]))
+
+    def _r_cut_matrix(self, state):
+        nt = state.ntypes
+        rc = np.zeros((nt, nt))
+        for i, a in enumerate(state.types):
+            for j, b in enumerate(state.types):
+                v = self.r_cut[(a, b)] if ((a, b) in self.r_cut or self.r_cut.default is not None) else None
+                if v is None:
+                    raise ValueError("r_cut not set for type pair (%s, %s)" % (a, b))
+                rc[i, j] = float(v)
+        return rc
+
+    def _r_on_matrix(self, state):
+        nt = state.ntypes
+        ro = np.zeros((nt, nt))
+        for i, a in enumerate(state.types):
+            for j, b in enumerate(state.types):
+                ro[i, j] = float(self.r_on[(a, b)])
+        return ro
+
+    def _fields(self, p):
+        return [float(p[k]) for k in self._param_schema]
+
+    # ---- attach: pack param_type tables and upload them (call stack 3.1 step 4) ----------
+    def attach(self, state):
+        if state.device.type != "cuda":
+            raise _lib.AzpError("%s runs on CUDA devices only (no CPU fallback)" % type(self).__name__)
+        self._state = state
+        bits = 8 * state.dtype.itemsize
+        nt = state.ntypes
+        psz = kernels.param_size(self._evaluator, bits)
+        table = np.zeros((nt * nt, psz), dtype=np.uint8)
+        for i, a in enumerate(state.types):
+            for j, b in enumerate(state.types):
+                if (a, b) not in self.params:
+                    raise ValueError("params not set for type pair (%s, %s)" % (a, b))
+                table[j * nt + i] = kernels.pack_params(self._evaluator, bits, self._fields(self.params[(a, b)]))
+        rc = self._r_cut_matrix(state).astype(state.dtype)
+        ro = self._r_on_matrix(state).astype(state.dtype)
+        dev = state.device
+        self._bits = bits
+        self._d_params = torch.from_numpy(table.reshape(-1).copy()).to(dev)
+        self._d_rcutsq = torch.from_numpy((rc * rc).T.reshape(-1).copy()).to(dev)
+        self._d_ronsq = torch.from_numpy((ro * ro).T.reshape(-1).copy()).to(dev)
+        n = state.N
+        self._force = torch.zeros((n, 4), dtype=state.torch_dtype, device=dev)
+        self._virial = torch.zeros((6, n), dtype=state.torch_dtype, device=dev)
+        self._torque = torch.zeros((n, 4), dtype=state.torch_dtype, device=dev)
+        self._computed = False
+        return self
+
+    _attach_hook = attach
+
+    def get_params_from_device(self, type_a, type_b):
+        """asDict()/toPython() of the uploaded ``param_type`` (what HOOMD reads back after attach)."""
+        st = self._state
+        nt = st.ntypes
+        psz = kernels.param_size(self._evaluator, self._bits)
+        idx = st.type_index(type_b) * nt + st.type_index(type_a)
+        raw = self._d_params.view(nt * nt, psz)[idx].cpu().numpy()
+        f = kernels.unpack_params(self._evaluator, self._bits, raw)
+        out = {}
+        for k, v in zip(self._param_schema, f):
+            out[k] = bool(v) if self._param_schema[k] is bool else float(v)
+        return out
+
+    # ---- compute -------------------------------------------------------------------------
+    def _extra_args(self, timestep):
+        return {}
+
+    def _args(self, timestep=None, compute_virial=True):
+        st = self._state
+        if st is None:
+            raise RuntimeError("potential is not attached to a State")
+        self.nlist.compute(st)
+        if self.nlist.storage_mode != "full":
+            raise RuntimeError("GPU pair potentials need a full neighbour list")
+        ts = st.timestep if timestep is None else int(timestep)
+        return kernels.fill_args(
+            box=st.box, pos=st.pos, n_neigh=self.nlist.n_neigh, nlist=self.nlist.nlist,
+            head_list=self.nlist.head_list, rcutsq=self._d_rcutsq, ronsq=self._d_ronsq,
+            ntypes=st.ntypes, force=self._force, virial=self._virial if compute_virial else None,
+            n_rows=st.N, shift_mode=_lib.SHIFT_MODES[self._mode], compute_virial=compute_virial,
+            block_size=self._launch_shape[0], threads_per_particle=self._launch_shape[1],
+            timestep=ts, size_neigh_list=self.nlist.size, **self._extra_args(ts))
+
+    def compute(self, timestep=None, compute_virial=True):
+        """``ForceCompute::compute(timestep)``: enqueue the kernel on the current stream."""
+        args = self._args(timestep, compute_virial)
+        with torch.cuda.device(self._state.device):
+            kernels.launch(self._family, self._evaluator, self._bits, args, self._d_params.data_ptr())
+        self._computed = True
+        return self
+
+    def tune_kernel_parameters(self, timestep=None, compute_virial=True):
+        """Scan (block_size, threads_per_particle) like HOOMD's autotuner and pin the fastest."""
+        args = self._args(timestep, compute_virial)
+        with torch.cuda.device(self._state.device):
+            b, t, ms = kernels.autotune(self._family, self._evaluator, self._bits, args,
+                                        self._d_params.data_ptr())
+        self._launch_shape = (b, t)
+        return b, t, ms
+
+    # ---- read-outs (hoomd.md.force.Force) ------------------------------------------------------
+    def _need(self):
+        if not getattr(self, "_computed", False):
+            self.compute()
+
+    @property
+    def forces(self):
+        self._need()
+        return self._force[:, :3].cpu().numpy()
+
+    @property
+    def energies(self):
+        self._need()
+        return self._force[:, 3].cpu().numpy()
+
+    @property
+    def energy(self):
+        self._need()
+        return float(self._force[:, 3].sum(dtype=torch.float64).item())
+
+    @property
+    def torques(self):
+        self._need()
+        return self._torque[:, :3].cpu().numpy()
+
+    @property
+    def virials(self):
+        self._need()
+        return self._virial.cpu().numpy().T.copy()
+
+
+class Colloid(Pair):
+    """Colloid (integrated Lennard-Jones) potential; params ``A, a_1, a_2, sigma``."""
+
+    _cpp_class_name = "PotentialPairColloid"
+    _evaluator = _lib.EV_COLLOID
+    _param_schema = {"A": float, "a_1": float, "a_2": float, "sigma": float}
+
+
+class ExpandedYukawa(Pair):
+    """Expanded Yukawa potential; params ``epsilon, kappa, delta``."""
+
+    _cpp_class_name = "PotentialPairExpandedYukawa"
+    _evaluator = _lib.EV_EXPANDED_YUKAWA
+    _param_schema = {"epsilon": float, "kappa": float, "delta": float}
+
+
+class Hertz(Pair):
+    """Hertz potential; params ``epsilon``."""
+
+    _cpp_class_name = "PotentialPairHertz"
+    _evaluator = _lib.EV_HERTZ
+    _param_schema = {"epsilon": float}
+
+
+class PerturbedLennardJones(Pair):
+    """Perturbed Lennard-Jones; params ``epsilon, sigma, attraction_scale_factor``."""
+
+    _cpp_class_name = "PotentialPairPerturbedLennardJones"
+    _evaluator = _lib.EV_PERTURBED_LENNARD_JONES
+    _param_schema = {"epsilon": float, "sigma": float, "attraction_scale_factor": float}
+
+
+class DPDGeneralWeight(Pair):
+    """DPD with generalised weight function and thermostat; params ``A, gamma, s``; ``kT``."""
+
+    _cpp_class_name = "PotentialPairDPDThermoGeneralWeight"
+    _evaluator = _lib.EV_DPD_GENERAL_WEIGHT
+    _family = _lib.FAMILY_DPD
+    _accepted_modes = ("none",)
+    _param_schema = {"A": float, "gamma": float, "s": float}
+
+    def __init__(self, nlist, kT, default_r_cut=None):
+        super().__init__(nlist=nlist, default_r_cut=default_r_cut, default_r_on=0, mode="none")
+        self.kT = kT
+
+    def _kT(self, timestep):
+        return float(self.kT(timestep)) if callable(self.kT) else float(self.kT)
+
+    def _extra_args(self, timestep):
+        st = self._state
+        return dict(vel=st.vel, tag=st.tag, seed=st.seed, dt=st.dt, kT=self._kT(timestep))
+
+
+class DPDGeneralWeightConservative(DPDGeneralWeight):
+    """``PotentialPairConservativeGeneralWeight``: the conservative part only
+    (reference src/export_PotentialPairDPDThermo.cc.inc:33-35)."""
+
+    _cpp_class_name = "PotentialPairConservativeGeneralWeight"
+    _family = _lib.FAMILY_PAIR
+
+    def __init__(self, nlist, default_r_cut=None):
+        super().__init__(nlist=nlist, kT=0.0, default_r_cut=default_r_cut)
+
+    def _extra_args(self, timestep):
+        return {}
+
+
+class AnisotropicPair(Pair):
+    """``hoomd.md.pair.aniso.AnisotropicPair`` work-alike: modes none/shift, no r_on."""
+
+    _family = _lib.FAMILY_ANISO
+    _accepted_modes = ("none", "shift")
+    is_anisotropic = True
+
+    def __init__(self, nlist, default_r_cut=None, mode="none"):
+        super().__init__(nlist, default_r_cut, 0.0, mode)
+
+    def _extra_args(self, timestep):
+        return dict(orientation=self._state.orientation, torque=self._torque)
+
+
+class TwoPatchMorse(AnisotropicPair):
+    """Two-patch Morse; params ``M_d, M_r, r_eq, omega, alpha, repulsion``."""
+
+    _cpp_class_name = "AnisoPotentialPairTwoPatchMorse"
+    _evaluator = _lib.EV_TWO_PATCH_MORSE
+    _param_schema = {"M_d": float, "M_r": float, "r_eq": float, "omega": float,
+                     "alpha": float, "repulsion": bool}

@@ -1,0 +1,202 @@
+/* azp_b200.h -- C ABI of the B200-native azplugins pair-force path.
+ *
+ * This is the drop-in boundary. Each entry point replaces one symbol that HOOMD-blue's host
+ * ForceCompute classes call and that azplugins instantiates (all paths relative to the
+ * reference tree):
+ *
+ *   azp_pair_forces_f32/_f64   <- hoomd::md::kernel::gpu_compute_pair_forces<E>(pair_args_t,
+ *                                 const E::param_type*), instantiated at
+ *                                 src/PotentialPairGPUKernel.cu.inc:25-28 for
+ *                                 E = PairEvaluator{Colloid,ExpandedYukawa,Hertz,
+ *                                 PerturbedLennardJones} (src/CMakeLists.txt:45-50) and, as
+ *                                 "PotentialPairConservativeGeneralWeight", for the DPD evaluator's
+ *                                 evalForceAndEnergy (src/export_PotentialPairDPDThermo.cc.inc:33-35)
+ *   azp_dpd_forces_f32/_f64    <- gpu_compute_dpd_forces<E>(dpd_pair_args_t, const param_type*),
+ *                                 src/PotentialPairDPDThermoGPUKernel.cu.inc:21-24
+ *   azp_aniso_forces_f32/_f64  <- gpu_compute_pair_aniso_forces<E>(a_pair_args_t,
+ *                                 const param_type*, const shape_type*),
+ *                                 src/AnisoPotentialPairGPUKernel.cu.inc:21-25
+ *   azp_param_size/pack/unpack <- E::param_type(pybind11::dict) / asDict() / toPython(), e.g.
+ *                                 src/PairEvaluatorPerturbedLennardJones.h:33-54
+ *
+ * The C++ shim azplugins_b200/csrc/hoomd_shim.h re-declares the three HOOMD templates on top of
+ * these functions; INTEGRATION.md shows the binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - all d_* pointers are DEVICE pointers owned by the caller (HOOMD GlobalArrays); the library
+ *     allocates nothing that outlives a call except a small per-device scratch for long rows;
+ *   - f32 entry points read/write float / float4 arrays, f64 double / double4 (HOOMD `Scalar`
+ *     for HOOMD_LONGREAL_SIZE 32 / 64);
+ *   - array layouts are HOOMD's: pos = (x,y,z,type bit-cast),
+ *     vel = (vx,vy,vz,mass), orientation = quaternion (s,x,y,z), force = (fx,fy,fz,energy),
+ *     torque = (tx,ty,tz,0), virial[k*pitch + i] with k = xx,xy,xz,yy,yz,zz;
+ *     n_neigh/nlist/head_list are NeighborListGPU's arrays in `full` storage mode;
+ *   - outputs are overwritten for every row (zeros for empty rows);
+ *   - every function returns a cudaError_t value as int (0 = success, 1 = cudaErrorInvalidValue
+ *     for bad arguments) and never throws; kernels are enqueued on `stream` and the call does
+ *     not synchronise;
+ *   - there is NO CPU fallback: without a CUDA device the compute entry points fail.
+ */
+#ifndef AZP_B200_H_
+#define AZP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C"
+    {
+#endif
+
+#define AZP_B200_ABI_VERSION 1
+
+/* evaluator ids */
+enum azp_evaluator
+    {
+    AZP_EV_PERTURBED_LENNARD_JONES = 0, /* src/PairEvaluatorPerturbedLennardJones.h */
+    AZP_EV_EXPANDED_YUKAWA = 1,         /* src/PairEvaluatorExpandedYukawa.h */
+    AZP_EV_COLLOID = 2,                 /* src/PairEvaluatorColloid.h */
+    AZP_EV_HERTZ = 3,                   /* src/PairEvaluatorHertz.h */
+    AZP_EV_DPD_GENERAL_WEIGHT = 4,      /* src/DPDPairEvaluatorGeneralWeight.h */
+    AZP_EV_TWO_PATCH_MORSE = 5,         /* src/AnisoPairEvaluatorTwoPatchMorse.h */
+    AZP_EV_COUNT = 6
+    };
+
+/* energy shift modes of md::PotentialPair */
+enum azp_shift_mode
+    {
+    AZP_SHIFT_NONE = 0,
+    AZP_SHIFT_SHIFT = 1,
+    AZP_SHIFT_XPLOR = 2
+    };
+
+/* HOOMD BoxDim flattened. Lengths are converted to Scalar inside the call and Linv = 1/L is
+ * formed in Scalar precision, as BoxDim does. The box is centred on the origin. */
+typedef struct azp_box
+    {
+    double L[3];
+    double tilt[3];      /* xy, xz, yz */
+    int32_t periodic[3]; /* per direction */
+    int32_t _pad;
+    } azp_box;
+
+/* Union of HOOMD's pair_args_t / dpd_pair_args_t / a_pair_args_t. Fields a
+ * family does not use may be NULL / 0. */
+typedef struct azp_pair_args
+    {
+    /* outputs */
+    void* d_force;         /* Scalar4[N] */
+    void* d_virial;        /* Scalar[6 * virial_pitch]; may be NULL when compute_virial == 0 */
+    void* d_torque;        /* Scalar4[N], aniso only */
+    uint64_t virial_pitch;
+    /* particle data, indexed by global particle index (local rows first, then ghosts) */
+    const void* d_pos;         /* Scalar4[>= row_offset + N, + ghosts] */
+    const void* d_vel;         /* Scalar4, DPD only */
+    const void* d_orientation; /* Scalar4, aniso only */
+    const uint32_t* d_tag;     /* DPD only */
+    /* neighbour list (full storage), indexed by row */
+    const uint32_t* d_n_neigh;
+    const uint32_t* d_nlist;
+    const uint64_t* d_head_list;
+    uint64_t size_neigh_list;
+    /* per type-pair tables, Index2D(ntypes)(i,j) = j*ntypes + i */
+    const void* d_rcutsq; /* Scalar[ntypes^2] */
+    const void* d_ronsq;  /* Scalar[ntypes^2], isotropic xplor only */
+    azp_box box;
+    uint32_t N;      /* rows to compute */
+    uint32_t ntypes;
+    uint32_t shift_mode;     /* azp_shift_mode; DPD ignores it, aniso accepts none/shift */
+    uint32_t compute_virial; /* 0/1 */
+    /* launch parameters (HOOMD's Autotuner<2> dimensions); 0 = let the library choose */
+    uint32_t block_size;
+    uint32_t threads_per_particle; /* power of two <= 32 */
+    /* DPD thermostat */
+    uint32_t seed;     /* uint16 range */
+    uint32_t _pad0;
+    uint64_t timestep; /* truncated to 32 bits like the reference evaluator does */
+    double deltaT;
+    double T;
+    /* Extensions for the multi-GPU particle-slice scheduler (0 / NULL = HOOMD behaviour):
+     * row r describes particle i = row_offset + r; outputs, n_neigh and head_list are indexed
+     * by r, gathered particle data by global index. d_row_ids, when set, lists the n_row_ids
+     * rows to compute (e.g. interior rows while the position exchange is in flight) and rows
+     * not listed are left untouched. */
+    uint32_t row_offset;
+    uint32_t n_row_ids;
+    const uint32_t* d_row_ids;
+    } azp_pair_args;
+
+/* library / device */
+int azp_abi_version(void);
+const char* azp_error_string(int code);
+const char* azp_evaluator_name(int evaluator); /* reference getName() strings */
+
+/* param_type staging: sizes match the reference structs (fp32/fp64): PLJ, Yukawa, Colloid, DPD
+ * 16/32, Hertz 4/8, TwoPatchMorse 24/48. `fields` order:
+ *   PLJ {epsilon, sigma, attraction_scale_factor}   Yukawa {epsilon, kappa, delta}
+ *   Colloid {A, a_1, a_2, sigma}   Hertz {epsilon}   DPD {A, gamma, s}
+ *   TwoPatchMorse {M_d, M_r, r_eq, omega, alpha, repulsion(0/1)}
+ * pack reproduces the roundings of the reference constructors; unpack those of asDict(). */
+int azp_param_num_fields(int evaluator);
+int azp_param_size(int evaluator, int scalar_bits);
+int azp_param_pack(int evaluator, int scalar_bits, const double* fields, void* out);
+int azp_param_unpack(int evaluator, int scalar_bits, const void* in, double* fields);
+
+/* force kernels; `stream` is a cudaStream_t (NULL = default stream) */
+int azp_pair_forces_f32(int evaluator, const azp_pair_args* args, const void* d_params, void* stream);
+int azp_pair_forces_f64(int evaluator, const azp_pair_args* args, const void* d_params, void* stream);
+int azp_dpd_forces_f32(int evaluator, const azp_pair_args* args, const void* d_params, void* stream);
+int azp_dpd_forces_f64(int evaluator, const azp_pair_args* args, const void* d_params, void* stream);
+int azp_aniso_forces_f32(int evaluator, const azp_pair_args* args, const void* d_params,
+                         const void* d_shape_params, void* stream);
+int azp_aniso_forces_f64(int evaluator, const azp_pair_args* args, const void* d_params,
+                         const void* d_shape_params, void* stream);
+
+/* Launch autotuner (HOOMD Autotuner<2> equivalent): times the (block_size, threads_per_particle)
+ * candidates on the given arguments with CUDA events, writes the fastest pair and its time.
+ * family: 0 pair, 1 dpd, 2 aniso. Synchronises the stream. */
+int azp_autotune(int family, int evaluator, int scalar_bits, const azp_pair_args* args,
+                 const void* d_params, void* stream, uint32_t* best_block, uint32_t* best_tpp,
+                 float* best_ms);
+
+/* Uniform(-1,1) value the DPD evaluator draws for a pair (host side; same code as the kernel).
+ * Exposes the RNG keying of src/DPDPairEvaluatorGeneralWeight.h:213-233 for parity tests. */
+double azp_dpd_alpha(int scalar_bits, uint32_t seed, uint32_t tag_i, uint32_t tag_j, uint64_t timestep);
+void azp_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+
+/* HOOMD-layout full neighbour list on the GPU (row "next" of SURVEY.md 8(f), used to feed the
+ * path): cell-list build of n_neigh / nlist / head_list with r_list = r_cut + buffer per type
+ * pair. Two calls: azp_nlist_count fills d_n_neigh; the caller turns per-type maxima into
+ * head_list (prefix sum of Nmax[type]); azp_nlist_fill writes the rows. d_cell_* are scratch
+ * arrays sized by azp_nlist_scratch_sizes. */
+typedef struct azp_nlist_args
+    {
+    const void* d_pos; /* Scalar4[N] */
+    uint32_t N;
+    uint32_t ntypes;
+    azp_box box;
+    const void* d_rlistsq; /* Scalar[ntypes^2] */
+    double r_list_max;
+    uint32_t* d_n_neigh;         /* [N] out (count) / in (fill) */
+    const uint64_t* d_head_list; /* [N] in (fill) */
+    uint32_t* d_nlist;           /* out (fill) */
+    uint32_t* d_cell_of;         /* [N] scratch */
+    uint32_t* d_cell_start;      /* [ncells + 1] scratch */
+    uint32_t* d_cell_order;      /* [N] scratch */
+    uint32_t cell_dim[3];        /* from azp_nlist_cell_dim */
+    uint32_t _pad;
+    } azp_nlist_args;
+
+int azp_nlist_cell_dim(const azp_box* box, double r_list_max, uint32_t dim[3]);
+int azp_nlist_bin_f32(const azp_nlist_args* args, void* stream);
+int azp_nlist_bin_f64(const azp_nlist_args* args, void* stream);
+int azp_nlist_count_f32(const azp_nlist_args* args, void* stream);
+int azp_nlist_count_f64(const azp_nlist_args* args, void* stream);
+int azp_nlist_fill_f32(const azp_nlist_args* args, void* stream);
+int azp_nlist_fill_f64(const azp_nlist_args* args, void* stream);
+
+#ifdef __cplusplus
+    }
+#endif
+
+#endif /* AZP_B200_H_ */

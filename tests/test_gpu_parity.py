@@ -1,0 +1,386 @@
+"""GPU parity proper: CUDA path (through the pair API and the C ABI) against the CPU oracle on
+the same seeded inputs and the same neighbour list. Budgets are BASELINE.json's: per-particle
+force/torque relative error <= 1e-5 (fp32) / 1e-10 (fp64); total energy and virial <= 1e-6
+(fp32) / 1e-10 (fp64). Error definitions: tests/helpers.py."""
+
+import numpy as np
+import pytest
+
+import helpers
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+SMALL_N = {"C1": 32000, "C2": 27000, "C3": 120000, "C4": 64000, "C5": 54000}
+
+
+def run_config(cfg, dtype, N=None, virial=True, modes=None, kinds=("best",), tpp=None,
+               tol_scale=1.0):
+    import azplugins_b200 as az
+    from azplugins_b200 import synth
+
+    wl = synth.CONFIGS[cfg](N=SMALL_N[cfg] if N is None else N)
+    state = wl.make_state(dtype=dtype)
+    nl = az.nlist.Cell(buffer=synth.BUFFER)
+    pots = wl.make_potentials(nl)
+    reports = []
+    for pot in pots:
+        for mode in (modes or [pot.mode]):
+            pot.mode = mode
+            pot.attach(state)
+            if tpp:
+                pot.kernel_parameters = tpp
+            pot.compute(compute_virial=virial)
+            arrays = nl.to_numpy()
+            for kind in kinds:
+                orc = oracle.load(kind, dtype)
+                ref = helpers.oracle_compute(orc, state, pot, arrays, virial=virial)
+                its = np.dtype(dtype).itemsize
+                rep = helpers.check_against_oracle(
+                    pot, ref, its, virial=virial,
+                    force_tol=helpers.FORCE_TOL[its] * tol_scale,
+                    total_tol=helpers.TOTAL_TOL[its] * tol_scale)
+                reports.append((cfg, type(pot).__name__, mode, kind, rep))
+    return reports, wl, state, nl, pots
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64], ids=["f32", "f64"])
+@pytest.mark.parametrize("cfg", ["C1", "C2", "C3", "C4", "C5"])
+def test_config_matches_oracle(cfg, dtype):
+    reports, *_ = run_config(cfg, dtype)
+    for r in reports:
+        print(r)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64], ids=["f32", "f64"])
+def test_fp32_and_fp64_against_fp64_truth(dtype):
+    """The CUDA result is also within budget of the fp64 oracle (HOOMD's default build)."""
+    import azplugins_b200 as az
+    from azplugins_b200 import synth
+
+    wl = synth.config2(N=27000)
+    state = wl.make_state(dtype=dtype)
+    nl = az.nlist.Cell(buffer=synth.BUFFER)
+    (pot,) = wl.make_potentials(nl)
+    pot.attach(state)
+    pot.compute()
+    arrays = nl.to_numpy()
+    state64 = wl.make_state(dtype=np.float64)
+    ref = helpers.oracle_compute(oracle.load("best", np.float64), state64, pot, arrays)
+    helpers.check_against_oracle(pot, ref, np.dtype(dtype).itemsize)
+
+
+@pytest.mark.parametrize("mode", ["none", "shift", "xplor"])
+@pytest.mark.parametrize("cls,params", [
+    ("PerturbedLennardJones", dict(epsilon=1.0, sigma=1.0, attraction_scale_factor=0.5)),
+    ("ExpandedYukawa", dict(epsilon=2.0, kappa=1.2, delta=0.15)),
+    ("Hertz", dict(epsilon=25.0)),
+    ("Colloid", dict(A=144.0, a_1=0.0, a_2=0.0, sigma=1.0)),
+])
+def test_shift_modes(cls, params, mode):
+    """none / shift / xplor (xplor is never exercised by the reference's tests; the oracle loop
+    defines it), fp32 and fp64, with r_on < r_cut."""
+    import azplugins_b200 as az
+    from azplugins_b200 import synth
+
+    wl = synth.config1(N=8000)
+    for dtype in (np.float32, np.float64):
+        state = wl.make_state(dtype=dtype)
+        nl = az.nlist.Cell(buffer=0.4)
+        pot = getattr(az.pair, cls)(nlist=nl, default_r_cut=2.5, default_r_on=2.0, mode=mode)
+        pot.params[("A", "A")] = params
+        pot.attach(state)
+        pot.compute()
+        ref = helpers.oracle_compute(oracle.load("best", dtype), state, pot, nl.to_numpy())
+        helpers.check_against_oracle(pot, ref, np.dtype(dtype).itemsize)
+
+
+def test_xplor_with_r_on_beyond_r_cut_is_shift():
+    import azplugins_b200 as az
+    from azplugins_b200 import synth
+
+    wl = synth.config1(N=4096)
+    state = wl.make_state(dtype=np.float64)
+    out = []
+    for mode, r_on in (("xplor", 3.0), ("shift", 0.0)):
+        nl = az.nlist.Cell(buffer=0.4)
+        pot = az.pair.PerturbedLennardJones(nlist=nl, default_r_cut=2.5, default_r_on=r_on, mode=mode)
+        pot.params[("A", "A")] = dict(epsilon=1.0, sigma=1.0, attraction_scale_factor=0.5)
+        pot.attach(state).compute()
+        out.append((pot.forces.copy(), pot.energies.copy()))
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+
+
+@pytest.mark.parametrize("tpp", [1, 2, 4, 8, 16, 32])
+@pytest.mark.parametrize("block", [32, 64, 128, 256, 512])
+def test_launch_shapes(tpp, block):
+    """Every (block_size, threads_per_particle) the autotuner may pick gives the same answer."""
+    reports, *_ = run_config("C2", np.float32, N=8000, tpp=(block, tpp))
+    assert reports
+
+
+def test_dpd_random_stream_matches_oracle():
+    """Thermostatted forces (kT > 0) agree pair-stream-for-pair-stream with the oracle: the
+    Philox keying (seed, min/max tag, 32-bit timestep) is the same on both sides. The drag and
+    random terms are large, so this fails loudly if a single draw differs."""
+    import azplugins_b200 as az
+    from azplugins_b200 import synth
+
+    for dtype in (np.float32, np.float64):
+        for s in (2.0, 0.5):
+            wl = synth.config4(N=27000, s=s)
+            wl.timestep = (7 << 32) + 1000  # upper bits must be ignored (32-bit truncation)
+            state = wl.make_state(dtype=dtype)
+            nl = az.nlist.Cell(buffer=0.4)
+            (pot,) = wl.make_potentials(nl)
+            pot.attach(state).compute()
+            ref = helpers.oracle_compute(oracle.load("best", dtype), state, pot, nl.to_numpy())
+            helpers.check_against_oracle(pot, ref, np.dtype(dtype).itemsize)
+            # and the stream really depends on seed and timestep
+            f0 = pot.forces.copy()
+            state.seed = 43
+            pot.compute()
+            assert np.abs(pot.forces - f0).max() > 1e-2
+            state.seed = 42
+            state.timestep += 1
+            pot.compute()
+            assert np.abs(pot.forces - f0).max() > 1e-2
+
+
+def test_dpd_conservative_class():
+    import azplugins_b200 as az
+    from azplugins_b200 import synth
+
+    wl = synth.config4(N=27000)
+    state = wl.make_state(dtype=np.float32)
+    nl = az.nlist.Cell(buffer=0.4)
+    pot = az.pair.DPDGeneralWeightConservative(nlist=nl, default_r_cut=1.0)
+    pot.params[("A", "A")] = dict(A=25.0, gamma=4.5, s=2.0)
+    pot.attach(state).compute()
+    ref = helpers.oracle_compute(oracle.load("best", np.float32), state, pot, nl.to_numpy())
+    helpers.check_against_oracle(pot, ref, 4)
+
+
+def test_multi_type_tables_and_excluded_pairs():
+    """Three types, asymmetric parameters per pair, one pair switched off with r_cut = 0."""
+    import azplugins_b200 as az
+
+    rng = np.random.default_rng(11)
+    n, rho = 6000, 0.6
+    L = (n / rho) ** (1 / 3)
+    xyz = rng.uniform(-L / 2, L / 2, size=(n, 3))
+    # push apart overlapping random points a little: drop pairs closer than 0.7
+    from scipy.spatial import cKDTree
+
+    tree = cKDTree(xyz + L / 2, boxsize=L)
+    bad = {j for i, j in tree.query_pairs(0.75)}
+    xyz = np.delete(xyz, sorted(bad), axis=0)
+    typeid = rng.integers(0, 3, size=len(xyz))
+    for dtype in (np.float32, np.float64):
+        state = az.State(az.Box.cube(L), ["A", "B", "C"], xyz, typeid=typeid, dtype=dtype)
+        nl = az.nlist.Cell(buffer=0.3)
+        pot = az.pair.ExpandedYukawa(nlist=nl, default_r_cut=2.5, mode="shift")
+        k = 0
+        for a in "ABC":
+            for b in "ABC":
+                if a <= b:
+                    pot.params[(a, b)] = dict(epsilon=1.0 + 0.5 * k, kappa=1.0 + 0.1 * k, delta=0.05 * k)
+                    k += 1
+        pot.r_cut[("A", "C")] = 0.0
+        pot.r_cut[("B", "B")] = 1.7
+        pot.attach(state).compute()
+        ref = helpers.oracle_compute(oracle.load("best", dtype), state, pot, nl.to_numpy())
+        helpers.check_against_oracle(pot, ref, np.dtype(dtype).itemsize)
+
+
+def test_edge_cases_empty_rows_tiny_systems_and_slab_box():
+    """N = 1 (empty row, output must be overwritten with zeros), N = 2 across a periodic face,
+    N not a multiple of the block, non-cubic box, one non-periodic direction."""
+    import torch
+
+    import azplugins_b200 as az
+
+    p = dict(epsilon=1.0, sigma=1.0, attraction_scale_factor=0.5)
+    # single particle: empty row -> zeros written over stale output
+    state = az.State(az.Box.cube(10.0), ["A"], [[0, 0, 0]], dtype=np.float32)
+    pot = az.pair.PerturbedLennardJones(nlist=az.nlist.Cell(buffer=0.4), default_r_cut=3.0)
+    pot.params[("A", "A")] = p
+    pot.attach(state)
+    pot._force.fill_(7.0)
+    pot._virial.fill_(7.0)
+    pot.compute()
+    assert not pot.forces.any() and not pot.energies.any() and not pot.virials.any()
+    # pair interacting through the periodic boundary (minimum image), all three axes
+    for axis in range(3):
+        for dtype in (np.float32, np.float64):
+            xyz = np.zeros((2, 3))
+            xyz[0, axis], xyz[1, axis] = -4.6, 4.5  # 0.9 apart through the face of L = 10
+            state = az.State(az.Box(10.0, 10.0, 10.0), ["A"], xyz, dtype=dtype)
+            nl = az.nlist.Cell(buffer=0.4)
+            pot = az.pair.PerturbedLennardJones(nlist=nl, default_r_cut=3.0)
+            pot.params[("A", "A")] = p
+            pot.attach(state).compute()
+            ref = helpers.oracle_compute(oracle.load("best", dtype), state, pot, nl.to_numpy())
+            assert nl.to_numpy()[0].tolist() == [1, 1]
+            helpers.check_against_oracle(pot, ref, np.dtype(dtype).itemsize)
+            assert abs(pot.forces[0, axis]) > 1.0
+    # non-cubic box, z not periodic, odd particle count
+    rng = np.random.default_rng(3)
+    n = 4099
+    box = az.Box(17.0, 21.0, 13.0, periodic=(True, True, False))
+    g = np.stack(np.meshgrid(np.arange(17), np.arange(21), np.arange(13), indexing="ij"), -1).reshape(-1, 3)
+    xyz = (g[rng.choice(len(g), n, replace=False)] + 0.5 + rng.uniform(-0.2, 0.2, (n, 3)))
+    xyz -= np.array([8.5, 10.5, 6.5])
+    for dtype in (np.float32, np.float64):
+        state = az.State(box, ["A"], xyz, dtype=dtype)
+        nl = az.nlist.Cell(buffer=0.4)
+        pot = az.pair.PerturbedLennardJones(nlist=nl, default_r_cut=2.5)
+        pot.params[("A", "A")] = p
+        pot.attach(state).compute()
+        ref = helpers.oracle_compute(oracle.load("best", dtype), state, pot, nl.to_numpy())
+        helpers.check_against_oracle(pot, ref, np.dtype(dtype).itemsize)
+    torch.cuda.synchronize()
+
+
+def test_triclinic_box_and_external_nlist():
+    """Tilted box: the list comes from the CPU builder (from_arrays path = HOOMD-owned arrays);
+    the kernel takes the general minimum-image branch."""
+    import azplugins_b200 as az
+
+    rng = np.random.default_rng(8)
+    n = 3000
+    L = 14.0
+    g = np.stack(np.meshgrid(*[np.arange(14)] * 3, indexing="ij"), -1).reshape(-1, 3)
+    frac = (g[rng.choice(len(g), n, replace=False)] + 0.5 + rng.uniform(-0.2, 0.2, (n, 3))) / 14.0 - 0.5
+    xy, xz, yz = 0.3, -0.2, 0.15
+    # fractional -> cartesian for a HOOMD triclinic box
+    z = frac[:, 2] * L
+    y = frac[:, 1] * L + yz * z
+    x = frac[:, 0] * L + xy * (frac[:, 1] * L) + xz * z
+    xyz = np.stack([x, y, z], 1)
+    for dtype in (np.float32, np.float64):
+        orc = oracle.load("best", dtype)
+        box = az.Box(L, L, L, xy=xy, xz=xz, yz=yz)
+        state = az.State(box, ["A"], xyz, dtype=dtype)
+        arrays = orc.build_nlist(state.pos.cpu().numpy(), [L] * 3, 2.9, tilt=(xy, xz, yz))
+        nl = az.nlist.NeighborList.from_arrays(*arrays)
+        pot = az.pair.ExpandedYukawa(nlist=nl, default_r_cut=2.5, mode="shift")
+        pot.params[("A", "A")] = dict(epsilon=1.0, kappa=1.0, delta=0.1)
+        pot.attach(state).compute()
+        ref = helpers.oracle_compute(orc, state, pot, arrays)
+        helpers.check_against_oracle(pot, ref, np.dtype(dtype).itemsize)
+
+
+def test_ghost_particles_row_offset_and_row_ids():
+    """Rows [0, N) only, neighbours may be ghosts (index >= N); and the scheduler extensions:
+    row_offset (a slice of rows) and d_row_ids (a subset of rows) reproduce the full result."""
+    import torch
+
+    import azplugins_b200 as az
+    from azplugins_b200 import _lib, kernels, synth
+
+    wl = synth.config1(N=8000)
+    n_ghost = 1500
+    state = az.State(wl.box, wl.types, wl.position, dtype=np.float32, n_ghost=n_ghost)
+    nl = az.nlist.Cell(buffer=0.4)
+    (pot,) = wl.make_potentials(nl)
+    pot.attach(state).compute()
+    N = state.N
+    assert N == 8000 - n_ghost and pot.forces.shape[0] == N
+    orc = oracle.load("best", np.float32)
+    ref = helpers.oracle_compute(orc, state, pot, nl.to_numpy(), n_rows=N)
+    helpers.check_against_oracle(pot, ref, 4, n_rows=N)
+    full = pot._force.clone()
+
+    # a slice of rows [lo, hi) with local outputs
+    lo, hi = 1000, 4321
+    f2 = torch.full((hi - lo, 4), 9.0, dtype=torch.float32, device=state.device)
+    args = kernels.fill_args(box=state.box, pos=state.pos, n_neigh=nl.n_neigh[lo:hi],
+                             nlist=nl.nlist, head_list=nl.head_list[lo:hi], rcutsq=pot._d_rcutsq,
+                             ronsq=pot._d_ronsq, ntypes=1, force=f2, n_rows=hi - lo, row_offset=lo)
+    kernels.launch(_lib.FAMILY_PAIR, pot._evaluator, 32, args, pot._d_params.data_ptr())
+    assert torch.equal(f2, full[lo:hi])
+
+    # a subset of rows: the others are left untouched
+    ids = torch.arange(0, N, 3, dtype=torch.int32, device=state.device)
+    f3 = torch.full((N, 4), 9.0, dtype=torch.float32, device=state.device)
+    args = kernels.fill_args(box=state.box, pos=state.pos, n_neigh=nl.n_neigh, nlist=nl.nlist,
+                             head_list=nl.head_list, rcutsq=pot._d_rcutsq, ronsq=pot._d_ronsq,
+                             ntypes=1, force=f3, n_rows=N, row_ids=ids)
+    kernels.launch(_lib.FAMILY_PAIR, pot._evaluator, 32, args, pot._d_params.data_ptr())
+    idl = ids.long()
+    assert torch.equal(f3[idl], full[idl])
+    mask = torch.ones(N, dtype=torch.bool, device=state.device)
+    mask[idl] = False
+    assert bool((f3[mask] == 9.0).all())
+
+
+def test_invalid_arguments_return_errors():
+    import azplugins_b200 as az
+    from azplugins_b200 import _lib, kernels, synth
+
+    wl = synth.config1(N=4096)
+    state = wl.make_state()
+    nl = az.nlist.Cell(buffer=0.4)
+    (pot,) = wl.make_potentials(nl)
+    pot.attach(state).compute()
+    for bad in (dict(threads_per_particle=3), dict(threads_per_particle=64), dict(block_size=100),
+                dict(block_size=2048), dict(shift_mode=5)):
+        args = pot._args()
+        for k, v in bad.items():
+            setattr(args, k, v)
+        with pytest.raises(_lib.AzpError):
+            kernels.launch(_lib.FAMILY_PAIR, pot._evaluator, 32, args, pot._d_params.data_ptr())
+    args = pot._args()
+    with pytest.raises(_lib.AzpError):  # DPD family without vel/tag
+        kernels.launch(_lib.FAMILY_DPD, _lib.EV_DPD_GENERAL_WEIGHT, 32, args, pot._d_params.data_ptr())
+    with pytest.raises(_lib.AzpError):  # wrong evaluator for the family
+        kernels.launch(_lib.FAMILY_ANISO, _lib.EV_HERTZ, 32, args, pot._d_params.data_ptr())
+    with pytest.raises(ValueError):
+        pot.mode = "bogus"
+    with pytest.raises(ValueError):
+        az.pair.DPDGeneralWeight(nlist=nl, kT=1.0).mode = "shift"
+
+
+def test_gpu_nlist_matches_cpu_builder():
+    """Row "next #1": the GPU cell-list builder returns the same neighbour sets as the CPU one."""
+    import azplugins_b200 as az
+    from azplugins_b200 import synth
+
+    for cfg, N in (("C2", 27000), ("C3", 120000)):
+        wl = synth.CONFIGS[cfg](N=N)
+        for dtype in (np.float32, np.float64):
+            state = wl.make_state(dtype=dtype)
+            nl = az.nlist.Cell(buffer=0.4)
+            pots = wl.make_potentials(nl)
+            nl.compute(state)
+            nn, lst, head = nl.to_numpy()
+            orc = oracle.load("port", dtype)
+            r_list = nl.r_cut_matrix(state) + 0.4
+            cn, cl, ch = orc.build_nlist(state.pos.cpu().numpy(), state.box.L, r_list,
+                                         ntypes=state.ntypes)
+            assert np.array_equal(nn, cn)
+            assert head[0] == 0 and (np.diff(head.astype(np.int64)) >= nn[:-1]).all()
+            for i in np.random.default_rng(0).choice(len(nn), 500, replace=False):
+                a = np.sort(lst[head[i]:head[i] + nn[i]])
+                b = cl[ch[i]:ch[i] + cn[i]]
+                assert np.array_equal(a, b)
+
+
+def test_nlist_rebuild_on_displacement():
+    import torch
+
+    import azplugins_b200 as az
+    from azplugins_b200 import synth
+
+    wl = synth.config1(N=4096)
+    state = wl.make_state()
+    nl = az.nlist.Cell(buffer=0.4)
+    wl.make_potentials(nl)
+    assert nl.compute(state) is True and nl.num_builds == 1
+    assert nl.compute(state) is False
+    state.pos[:, 0] += 0.05
+    assert nl.compute(state) is False  # moved less than buffer / 2
+    state.pos[10, 1] += 0.25
+    assert nl.compute(state) is True and nl.num_builds == 2
+    torch.cuda.synchronize()
