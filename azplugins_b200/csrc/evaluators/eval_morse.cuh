@@ -113,8 +113,8 @@ template<class S> class AnisoPairEvaluatorTwoPatchMorse
         const S rsq = dr.x * dr.x + dr.y * dr.y + dr.z * dr.z;
         if (rsq > rcutsq) // the reference rejects only strictly-greater (:135)
             return false;
-        const S rinv = fast::rsqrt(rsq);
-        const S r = rsq * rinv;
+        S r, rinv;
+        fast::sqrt_and_rsqrt(rsq, r, rinv);
         const Vec3<S> u {dr.x * rinv, dr.y * rinv, dr.z * rinv};
         const Vec3<S> ni = patch_director(quat_i);
         const Vec3<S> nj = patch_director(quat_j);

@@ -68,7 +68,8 @@ inline void nlist_pass(int pass,
                        unsigned int* n_neigh,
                        const uint64_t* head_list,
                        unsigned int* nlist,
-                       int nthreads)
+                       int nthreads,
+                       unsigned int n_rows)
     {
     S rmax = 0;
     for (unsigned int t = 0; t < ntypes * ntypes; ++t)
@@ -76,7 +77,7 @@ inline void nlist_pass(int pass,
     CellGrid<S> g;
     build_grid(g, N, pos, b, rmax);
 #pragma omp parallel for schedule(dynamic, 64) num_threads(nthreads > 0 ? nthreads : 1)
-    for (long long ii = 0; ii < (long long)N; ++ii)
+    for (long long ii = 0; ii < (long long)(n_rows ? n_rows : N); ++ii)
         {
         const unsigned int i = (unsigned int)ii;
         const S* pi = pos + 4 * size_t(i);

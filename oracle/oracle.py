@@ -151,7 +151,7 @@ class Oracle:
                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                      ctypes.c_uint32, ctypes.c_void_p, ctypes.c_int,
                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
-                                     ctypes.c_int]
+                                     ctypes.c_int, ctypes.c_uint32]
         if kind == "port":
             lib.oracle_pack_params.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         else:
@@ -255,10 +255,11 @@ class Oracle:
 
     # ---- neighbour list ------------------------------------------------------------------
     def build_nlist(self, pos, L, r_list, ntypes=1, tilt=(0, 0, 0), periodic=(1, 1, 1),
-                    half=False, nthreads=0, row_align=8):
+                    half=False, nthreads=0, row_align=8, n_rows=0):
         """HOOMD-layout list. ``r_list``: scalar or (ntypes, ntypes) array of r_cut + buffer.
         Returns (n_neigh u32[N], nlist u32[size], head_list u64[N]). Row capacity is the per-type
-        maximum rounded up to ``row_align`` (HOOMD: head_list = prefix sum of Nmax[type])."""
+        maximum rounded up to ``row_align`` (HOOMD: head_list = prefix sum of Nmax[type]).
+        ``n_rows`` > 0 builds only rows [0, n_rows) (the others stay empty): bounded CPU samples."""
         pos = np.ascontiguousarray(pos, dtype=self.dtype)
         N = pos.shape[0]
         rl = np.broadcast_to(np.asarray(r_list, dtype=np.float64), (ntypes, ntypes))
@@ -270,7 +271,7 @@ class Oracle:
         n_neigh = np.zeros(N, dtype=np.uint32)
         self.lib.oracle_nlist(0, N, pos.ctypes.data, Ld.ctypes.data, td.ctypes.data,
                               pd.ctypes.data, ntypes, rlsq.ctypes.data, int(half),
-                              n_neigh.ctypes.data, None, None, nt)
+                              n_neigh.ctypes.data, None, None, nt, n_rows)
         types = particle_types(pos)
         nmax = np.zeros(ntypes, dtype=np.uint64)
         for t in range(ntypes):
@@ -278,6 +279,8 @@ class Oracle:
             m = int(sel.max()) if sel.size else 0
             nmax[t] = (m + row_align - 1) // row_align * row_align if row_align > 1 else m
         cap = nmax[types]
+        if n_rows:
+            cap[n_rows:] = 0
         head = np.zeros(N, dtype=np.uint64)
         if N > 1:
             np.cumsum(cap[:-1], out=head[1:])
@@ -285,7 +288,7 @@ class Oracle:
         nlist = np.zeros(max(size, 1), dtype=np.uint32)
         self.lib.oracle_nlist(1, N, pos.ctypes.data, Ld.ctypes.data, td.ctypes.data,
                               pd.ctypes.data, ntypes, rlsq.ctypes.data, int(half),
-                              n_neigh.ctypes.data, head.ctypes.data, nlist.ctypes.data, nt)
+                              n_neigh.ctypes.data, head.ctypes.data, nlist.ctypes.data, nt, n_rows)
         return n_neigh, nlist, head
 
     # ---- force loops ---------------------------------------------------------------------

@@ -509,7 +509,8 @@ extern "C"
                      uint32_t* n_neigh,
                      const uint64_t* head_list,
                      uint32_t* nlist,
-                     int nthreads)
+                     int nthreads,
+                     uint32_t n_rows)
         {
         Box<S> b;
         for (int d = 0; d < 3; ++d)
@@ -520,7 +521,7 @@ extern "C"
             }
         b.xy = S(tilt[0]), b.xz = S(tilt[1]), b.yz = S(tilt[2]);
         nlist_pass<S>(pass, N, static_cast<const S*>(pos), b, ntypes,
-                      static_cast<const S*>(rlistsq), half, n_neigh, head_list, nlist, nthreads);
+                      static_cast<const S*>(rlistsq), half, n_neigh, head_list, nlist, nthreads, n_rows);
         return 0;
         }
 
