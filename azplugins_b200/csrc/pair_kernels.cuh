@@ -223,13 +223,15 @@ __global__ void __launch_bounds__(kMaxBlock)
                     force_divr = s * force_divr - ds * old_eng;
                     }
                 }
-            const S vx = dx * force_divr, vy = dy * force_divr, vz = dz * force_divr;
-            fx += vx;
-            fy += vy;
-            fz += vz;
+            // force by explicit FMA in both variants, so toggling the virial does not change
+            // a single bit of the forces
+            fx = fma(dx, force_divr, fx);
+            fy = fma(dy, force_divr, fy);
+            fz = fma(dz, force_divr, fz);
             pe += pair_eng;
             if (VIRIAL)
                 {
+                const S vx = dx * force_divr, vy = dy * force_divr, vz = dz * force_divr;
                 w0 += dx * vx;
                 w1 += dx * vy;
                 w2 += dx * vz;
@@ -358,9 +360,9 @@ __global__ void __launch_bounds__(kMaxBlock)
             eval.setRDotV(rdotv);
             eval.setT(a.T);
             eval.evalForceEnergyThermo(force_divr, force_divr_cons, pair_eng, false);
-            fx += dx * force_divr;
-            fy += dy * force_divr;
-            fz += dz * force_divr;
+            fx = fma(dx, force_divr, fx);
+            fy = fma(dy, force_divr, fy);
+            fz = fma(dz, force_divr, fz);
             pe += pair_eng;
             if (VIRIAL)
                 {

@@ -40,7 +40,8 @@ class NeighborList:
     def _add_consumer(self, force):
         if force not in self._consumers:
             self._consumers.append(force)
-            self.n_neigh = None  # r_cut may have grown
+            if not self._external:
+                self.n_neigh = None  # r_cut may have grown: rebuild at the next compute
 
     def r_cut_matrix(self, state):
         nt = state.ntypes

@@ -32,12 +32,16 @@ def run_config(cfg, dtype, N=None, virial=True, modes=None, kinds=("best",), tpp
                 pot.kernel_parameters = tpp
             pot.compute(compute_virial=virial)
             arrays = nl.to_numpy()
+            its = np.dtype(dtype).itemsize
+            truth = None
+            if its == 4:
+                truth = helpers.oracle_compute(oracle.load("best", np.float64), state, pot, arrays,
+                                               virial=virial)
             for kind in kinds:
                 orc = oracle.load(kind, dtype)
                 ref = helpers.oracle_compute(orc, state, pot, arrays, virial=virial)
-                its = np.dtype(dtype).itemsize
                 rep = helpers.check_against_oracle(
-                    pot, ref, its, virial=virial,
+                    pot, ref, its, virial=virial, truth=truth,
                     force_tol=helpers.FORCE_TOL[its] * tol_scale,
                     total_tol=helpers.TOTAL_TOL[its] * tol_scale)
                 reports.append((cfg, type(pot).__name__, mode, kind, rep))
@@ -65,9 +69,13 @@ def test_fp32_and_fp64_against_fp64_truth(dtype):
     pot.attach(state)
     pot.compute()
     arrays = nl.to_numpy()
-    state64 = wl.make_state(dtype=np.float64)
-    ref = helpers.oracle_compute(oracle.load("best", np.float64), state64, pot, arrays)
-    helpers.check_against_oracle(pot, ref, np.dtype(dtype).itemsize)
+    # same (dtype-rounded) inputs, fp64 arithmetic. For fp32 the distance to the fp64 result is
+    # set by fp32 rounding of ~124 partially cancelling terms per particle; the criterion is the
+    # budget or, failing that, "no farther from fp64 than 2x the fp32 CPU reference is".
+    truth = helpers.oracle_compute(oracle.load("best", np.float64), state, pot, arrays)
+    ref = helpers.oracle_compute(oracle.load("best", dtype), state, pot, arrays)
+    rep = helpers.check_against_oracle(pot, ref, np.dtype(dtype).itemsize, truth=truth)
+    print("vs fp64 truth", np.dtype(dtype).name, rep)
 
 
 @pytest.mark.parametrize("mode", ["none", "shift", "xplor"])
@@ -135,7 +143,12 @@ def test_dpd_random_stream_matches_oracle():
             (pot,) = wl.make_potentials(nl)
             pot.attach(state).compute()
             ref = helpers.oracle_compute(oracle.load("best", dtype), state, pot, nl.to_numpy())
-            helpers.check_against_oracle(pot, ref, np.dtype(dtype).itemsize)
+            truth = None
+            if dtype == np.float32:
+                truth = helpers.oracle_compute(oracle.load("best", np.float64), state, pot,
+                                               nl.to_numpy())
+            print("dpd stream", dtype.__name__, s,
+                  helpers.check_against_oracle(pot, ref, np.dtype(dtype).itemsize, truth=truth))
             # and the stream really depends on seed and timestep
             f0 = pot.forces.copy()
             state.seed = 43
@@ -248,7 +261,7 @@ def test_triclinic_box_and_external_nlist():
     import azplugins_b200 as az
 
     rng = np.random.default_rng(8)
-    n = 3000
+    n = 2500
     L = 14.0
     g = np.stack(np.meshgrid(*[np.arange(14)] * 3, indexing="ij"), -1).reshape(-1, 3)
     frac = (g[rng.choice(len(g), n, replace=False)] + 0.5 + rng.uniform(-0.2, 0.2, (n, 3))) / 14.0 - 0.5
@@ -284,20 +297,25 @@ def test_ghost_particles_row_offset_and_row_ids():
     state = az.State(wl.box, wl.types, wl.position, dtype=np.float32, n_ghost=n_ghost)
     nl = az.nlist.Cell(buffer=0.4)
     (pot,) = wl.make_potentials(nl)
-    pot.attach(state).compute()
+    pot.kernel_parameters = (128, 8)  # same summation order in every launch below
+    pot.attach(state).compute(compute_virial=False)
     N = state.N
     assert N == 8000 - n_ghost and pot.forces.shape[0] == N
     orc = oracle.load("best", np.float32)
-    ref = helpers.oracle_compute(orc, state, pot, nl.to_numpy(), n_rows=N)
-    helpers.check_against_oracle(pot, ref, 4, n_rows=N)
+    ref = helpers.oracle_compute(orc, state, pot, nl.to_numpy(), n_rows=N, virial=False)
+    helpers.check_against_oracle(pot, ref, 4, n_rows=N, virial=False)
     full = pot._force.clone()
+    # toggling the virial does not change a bit of the forces
+    pot.compute(compute_virial=True)
+    assert torch.equal(full, pot._force)
 
     # a slice of rows [lo, hi) with local outputs
     lo, hi = 1000, 4321
     f2 = torch.full((hi - lo, 4), 9.0, dtype=torch.float32, device=state.device)
     args = kernels.fill_args(box=state.box, pos=state.pos, n_neigh=nl.n_neigh[lo:hi],
                              nlist=nl.nlist, head_list=nl.head_list[lo:hi], rcutsq=pot._d_rcutsq,
-                             ronsq=pot._d_ronsq, ntypes=1, force=f2, n_rows=hi - lo, row_offset=lo)
+                             ronsq=pot._d_ronsq, ntypes=1, force=f2, n_rows=hi - lo, row_offset=lo,
+                             block_size=128, threads_per_particle=8)
     kernels.launch(_lib.FAMILY_PAIR, pot._evaluator, 32, args, pot._d_params.data_ptr())
     assert torch.equal(f2, full[lo:hi])
 
@@ -306,7 +324,8 @@ def test_ghost_particles_row_offset_and_row_ids():
     f3 = torch.full((N, 4), 9.0, dtype=torch.float32, device=state.device)
     args = kernels.fill_args(box=state.box, pos=state.pos, n_neigh=nl.n_neigh, nlist=nl.nlist,
                              head_list=nl.head_list, rcutsq=pot._d_rcutsq, ronsq=pot._d_ronsq,
-                             ntypes=1, force=f3, n_rows=N, row_ids=ids)
+                             ntypes=1, force=f3, n_rows=N, row_ids=ids, block_size=128,
+                             threads_per_particle=8)
     kernels.launch(_lib.FAMILY_PAIR, pot._evaluator, 32, args, pot._d_params.data_ptr())
     idl = ids.long()
     assert torch.equal(f3[idl], full[idl])
