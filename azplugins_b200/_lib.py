@@ -79,6 +79,8 @@ class AzpNlistArgs(ctypes.Structure):
         ("d_cell_start", ctypes.c_void_p),
         ("d_cell_order", ctypes.c_void_p),
         ("cell_dim", ctypes.c_uint32 * 3),
+        ("row_offset", ctypes.c_uint32),
+        ("n_rows", ctypes.c_uint32),
         ("_pad", ctypes.c_uint32),
     ]
 

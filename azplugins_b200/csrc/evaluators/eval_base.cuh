@@ -12,6 +12,14 @@
 // the loop-invariant parts hoisted. ContractEvaluator<E> below adapts any evaluator that only
 // follows the reference contract (cache_type = param_type).
 //
+// Kernel fast path. The kernels test the cutoff themselves (they need rsq < rcutsq to skip the
+// whole evaluation and the accumulation), so each evaluator also exposes
+//   static disabled(cache)   -- the "potential scaled to zero" clause of the reference test
+//                               (e.g. epsilon == 0); staged as an effective r_cut^2 of 0 so the
+//                               single compare rsq < rcutsq covers both clauses;
+//   evalPair(force_divr, pair_eng, energy_shift) -- the body of evalForceAndEnergy without the
+//                               test. evalForceAndEnergy == test + evalPair.
+//
 // "Zero on reject": like HOOMD's GPU driver, the kernels ignore the bool and rely on force_divr /
 // pair_eng being left untouched (0) when a pair is rejected.
 #ifndef AZP_EVAL_BASE_CUH_
@@ -76,6 +84,16 @@ template<class E, class S> class ContractEvaluator
     AZP_D bool evalForceAndEnergy(S& force_divr, S& pair_eng, bool energy_shift)
         {
         return m_eval.evalForceAndEnergy(force_divr, pair_eng, energy_shift);
+        }
+    // kernel-side entry points (see "kernel fast path" below): a contract-only evaluator keeps
+    // its own cutoff / zero-parameter tests
+    AZP_HD static bool disabled(const cache_type&)
+        {
+        return false;
+        }
+    AZP_D void evalPair(S& force_divr, S& pair_eng, bool energy_shift)
+        {
+        m_eval.evalForceAndEnergy(force_divr, pair_eng, energy_shift);
         }
 
     private:

@@ -35,7 +35,7 @@ template<class S> class PairEvaluatorColloid : public PairEvaluatorBase<S>
         ColloidColloid = 2
         };
 
-    struct cache_type
+    struct alignas(16) cache_type
         {
         S A;
         S sigma_3;
@@ -164,9 +164,23 @@ template<class S> class PairEvaluatorColloid : public PairEvaluatorBase<S>
         {
         }
 
-    AZP_D bool evalForceAndEnergy(S& force_divr, S& pair_eng, bool)
+    AZP_HD static bool disabled(const cache_type& c)
         {
-        if (this->rsq < this->rcutsq && c.A != S(0))
+        return c.A == S(0);
+        }
+
+    AZP_D bool evalForceAndEnergy(S& force_divr, S& pair_eng, bool energy_shift)
+        {
+        if (this->rsq < this->rcutsq && !disabled(c))
+            {
+            evalPair(force_divr, pair_eng, energy_shift);
+            return true;
+            }
+        return false;
+        }
+
+    AZP_D void evalPair(S& force_divr, S& pair_eng, bool)
+        {
             {
             S e;
             if (c.coupling == SolventSolvent)
@@ -176,9 +190,7 @@ template<class S> class PairEvaluatorColloid : public PairEvaluatorBase<S>
             else
                 e = colloidColloid<true>(c, this->rsq, force_divr);
             pair_eng = e - c.e_cut;
-            return true;
             }
-        return false;
         }
 
     static const char* getName()

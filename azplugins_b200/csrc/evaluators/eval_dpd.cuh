@@ -27,7 +27,7 @@ template<class S> class DPDPairEvaluatorGeneralWeight : public PairEvaluatorBase
         S s;
         };
 
-    struct cache_type
+    struct alignas(16) cache_type
         {
         S A;
         S gamma;
@@ -75,22 +75,41 @@ template<class S> class DPDPairEvaluatorGeneralWeight : public PairEvaluatorBase
         m_dot = dot;
         }
 
-    AZP_D bool evalForceAndEnergy(S& force_divr, S& pair_eng, bool)
+    AZP_HD static bool disabled(const cache_type&)
+        {
+        return false;
+        }
+
+    AZP_D bool evalForceAndEnergy(S& force_divr, S& pair_eng, bool energy_shift)
         {
         if (this->rsq < this->rcutsq)
             {
-            const S rinv = fast::rsqrt(this->rsq);
-            const S r = this->rsq * rinv;
-            force_divr = c.A * (rinv - c.rcut_inv);
-            pair_eng = c.A * (c.rcut - r) - S(0.5) * c.A * c.rcut_inv * (this->rcutsq - this->rsq);
+            evalPair(force_divr, pair_eng, energy_shift);
             return true;
             }
         return false;
         }
 
-    AZP_D bool evalForceEnergyThermo(S& force_divr, S& force_divr_cons, S& pair_eng, bool)
+    AZP_D void evalPair(S& force_divr, S& pair_eng, bool)
+        {
+        const S rinv = fast::rsqrt(this->rsq);
+        const S r = this->rsq * rinv;
+        force_divr = c.A * (rinv - c.rcut_inv);
+        pair_eng = c.A * (c.rcut - r) - S(0.5) * c.A * c.rcut_inv * (this->rcutsq - this->rsq);
+        }
+
+    AZP_D bool evalForceEnergyThermo(S& force_divr, S& force_divr_cons, S& pair_eng, bool energy_shift)
         {
         if (this->rsq < this->rcutsq)
+            {
+            evalThermoPair(force_divr, force_divr_cons, pair_eng, energy_shift);
+            return true;
+            }
+        return false;
+        }
+
+    AZP_D void evalThermoPair(S& force_divr, S& force_divr_cons, S& pair_eng, bool)
+        {
             {
             const S rinv = fast::rsqrt(this->rsq);
             const S r = this->rsq * rinv;
@@ -103,9 +122,7 @@ template<class S> class DPDPairEvaluatorGeneralWeight : public PairEvaluatorBase
             f += c.noise * wR * alpha;
             force_divr = f;
             pair_eng = c.A * (c.rcut - r) - S(0.5) * c.A * c.rcut_inv * (this->rcutsq - this->rsq);
-            return true;
             }
-        return false;
         }
 
     static const char* getName()

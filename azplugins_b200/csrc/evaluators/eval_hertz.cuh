@@ -17,7 +17,7 @@ template<class S> class PairEvaluatorHertz : public PairEvaluatorBase<S>
         S epsilon;
         };
 
-    struct cache_type
+    struct alignas(16) cache_type
         {
         S epsilon;
         S rcut_inv; // 1 / sqrt(rcutsq), hoisted per type pair
@@ -36,9 +36,23 @@ template<class S> class PairEvaluatorHertz : public PairEvaluatorBase<S>
         {
         }
 
-    AZP_D bool evalForceAndEnergy(S& force_divr, S& pair_eng, bool)
+    AZP_HD static bool disabled(const cache_type& c)
         {
-        if (this->rsq < this->rcutsq && c.epsilon != S(0))
+        return c.epsilon == S(0);
+        }
+
+    AZP_D bool evalForceAndEnergy(S& force_divr, S& pair_eng, bool energy_shift)
+        {
+        if (this->rsq < this->rcutsq && !disabled(c))
+            {
+            evalPair(force_divr, pair_eng, energy_shift);
+            return true;
+            }
+        return false;
+        }
+
+    AZP_D void evalPair(S& force_divr, S& pair_eng, bool)
+        {
             {
             const S rinv = fast::rsqrt(this->rsq);
             const S r = this->rsq * rinv;
@@ -47,9 +61,7 @@ template<class S> class PairEvaluatorHertz : public PairEvaluatorBase<S>
             const S e32 = c.epsilon * x * fast::sqrt(x);
             force_divr = S(2.5) * e32 * rinv * c.rcut_inv;
             pair_eng = e32 * x;
-            return true;
             }
-        return false;
         }
 
     static const char* getName()

@@ -48,7 +48,7 @@ template<class S> class AnisoPairEvaluatorTwoPatchMorse
         };
     typedef AnisoShapeParametersEmpty shape_type;
 
-    struct cache_type
+    struct alignas(16) cache_type
         {
         S M_d;
         S M_rinv;
@@ -108,11 +108,23 @@ template<class S> class AnisoPairEvaluatorTwoPatchMorse
         return true;
         }
 
-    AZP_D bool evaluate(Vec3<S>& force, S& pair_eng, bool, Vec3<S>& torque_i, Vec3<S>& torque_j)
+    AZP_HD static bool disabled(const cache_type&)
+        {
+        return false;
+        }
+
+    AZP_D bool evaluate(Vec3<S>& force, S& pair_eng, bool energy_shift, Vec3<S>& torque_i, Vec3<S>& torque_j)
         {
         const S rsq = dr.x * dr.x + dr.y * dr.y + dr.z * dr.z;
         if (rsq > rcutsq) // the reference rejects only strictly-greater (:135)
             return false;
+        evaluatePair(rsq, force, pair_eng, energy_shift, torque_i, torque_j);
+        return true;
+        }
+
+    // body of evaluate() for a pair already known to satisfy rsq <= rcutsq
+    AZP_D void evaluatePair(S rsq, Vec3<S>& force, S& pair_eng, bool, Vec3<S>& torque_i, Vec3<S>& torque_j)
+        {
         S r, rinv;
         fast::sqrt_and_rsqrt(rsq, r, rinv);
         const Vec3<S> u {dr.x * rinv, dr.y * rinv, dr.z * rinv};
@@ -152,7 +164,6 @@ template<class S> class AnisoPairEvaluatorTwoPatchMorse
         torque_i = Vec3<S> {dU_dgi * ci.x, dU_dgi * ci.y, dU_dgi * ci.z};
         torque_j = Vec3<S> {dU_dgj * cj.x, dU_dgj * cj.y, dU_dgj * cj.z};
         pair_eng = (UM - c.U_cut) * OiOj;
-        return true;
         }
 
     static const char* getName()

@@ -22,7 +22,7 @@ template<class S> class PairEvaluatorPerturbedLennardJones : public PairEvaluato
         S rwcasq;
         };
 
-    struct cache_type
+    struct alignas(16) cache_type
         {
         S lj1;    // 4 eps sigma^12
         S lj2;    // 4 eps sigma^6
@@ -60,9 +60,23 @@ template<class S> class PairEvaluatorPerturbedLennardJones : public PairEvaluato
         {
         }
 
-    AZP_D bool evalForceAndEnergy(S& force_divr, S& pair_eng, bool)
+    AZP_HD static bool disabled(const cache_type& c)
         {
-        if (this->rsq < this->rcutsq && c.lj1 != S(0))
+        return c.lj1 == S(0);
+        }
+
+    AZP_D bool evalForceAndEnergy(S& force_divr, S& pair_eng, bool energy_shift)
+        {
+        if (this->rsq < this->rcutsq && !disabled(c))
+            {
+            evalPair(force_divr, pair_eng, energy_shift);
+            return true;
+            }
+        return false;
+        }
+
+    AZP_D void evalPair(S& force_divr, S& pair_eng, bool)
+        {
             {
             const S r2inv = fast::rcp(this->rsq);
             const S r6inv = r2inv * r2inv * r2inv;
@@ -77,9 +91,7 @@ template<class S> class PairEvaluatorPerturbedLennardJones : public PairEvaluato
                 }
             force_divr = f;
             pair_eng = e - c.e_cut;
-            return true;
             }
-        return false;
         }
 
     static const char* getName()

@@ -18,12 +18,13 @@ template<class S> class PairEvaluatorExpandedYukawa : public PairEvaluatorBase<S
         S delta;
         };
 
-    struct cache_type
+    struct alignas(16) cache_type
         {
         S epsilon;
         S kappa;
         S delta;
         S e_cut; // eps exp(-kappa (r_cut - delta)) / (r_cut - delta) when shifting, else 0
+        S neg_kappa_scaled; // -kappa * log2(e) (fp32: argument of ex2) or -kappa (fp64)
         };
 
     AZP_HD static cache_type make_cache(const param_type& p, S rcutsq, bool energy_shift)
@@ -32,6 +33,7 @@ template<class S> class PairEvaluatorExpandedYukawa : public PairEvaluatorBase<S
         c.epsilon = p.epsilon;
         c.kappa = p.kappa;
         c.delta = p.delta;
+        c.neg_kappa_scaled = fast::exp_scale(-p.kappa);
         c.e_cut = S(0);
         if (energy_shift)
             {
@@ -47,20 +49,32 @@ template<class S> class PairEvaluatorExpandedYukawa : public PairEvaluatorBase<S
         {
         }
 
-    AZP_D bool evalForceAndEnergy(S& force_divr, S& pair_eng, bool)
+    AZP_HD static bool disabled(const cache_type& c)
         {
-        if (this->rsq < this->rcutsq && c.epsilon != S(0))
+        return c.epsilon == S(0);
+        }
+
+    AZP_D bool evalForceAndEnergy(S& force_divr, S& pair_eng, bool energy_shift)
+        {
+        if (this->rsq < this->rcutsq && !disabled(c))
+            {
+            evalPair(force_divr, pair_eng, energy_shift);
+            return true;
+            }
+        return false;
+        }
+
+    AZP_D void evalPair(S& force_divr, S& pair_eng, bool)
+        {
             {
             const S rinv = fast::rsqrt(this->rsq);
             const S r = this->rsq * rinv;
             const S rd = r - c.delta;
             const S rdinv = fast::rcp(rd);
-            const S e = c.epsilon * fast::exp(-c.kappa * rd) * rdinv;
+            const S e = c.epsilon * fast::exp_prescaled(c.neg_kappa_scaled * rd) * rdinv;
             force_divr = e * (c.kappa + rdinv) * rinv;
             pair_eng = e - c.e_cut;
-            return true;
             }
-        return false;
         }
 
     static const char* getName()

@@ -84,8 +84,10 @@ inline cudaError_t choose_shape(const azp_pair_args& a, LaunchShape& s)
         {
         const unsigned int rows = a.N ? a.N : 1u;
         const double mean_cap = a.size_neigh_list ? double(a.size_neigh_list) / rows : 64.0;
+        // rows are consumed four entries per lane per trip: ~48+ entries per lane keeps the
+        // fixed per-thread prologue and the shuffle reduction under 10 % of the row
         tpp = 1;
-        while (tpp < 32u && mean_cap / tpp > 18.0)
+        while (tpp < 32u && mean_cap / tpp > 80.0)
             tpp <<= 1;
         }
     if (!is_pow2(tpp) || tpp > 32u)
@@ -136,10 +138,10 @@ template<class K> inline cudaError_t ensure_smem(K kernel, size_t bytes)
 template<class E, class S, bool XPLOR, bool VIRIAL, bool NT1>
 inline cudaError_t launch_pair_variant(const KernelArgs<S>& k, const void* d_params, const LaunchShape& s, cudaStream_t stream)
     {
-    typedef typename E::cache_type Cache;
+    typedef IsoFamily<E, S, XPLOR, VIRIAL, NT1> Fam;
     const size_t ntp = NT1 ? 1 : size_t(k.ntypes) * k.ntypes;
-    const size_t smem = ntp * sizeof(Cache) + (ntp + 1) * sizeof(S) + (XPLOR ? ntp * sizeof(XplorEntry<S>) : 0) + 16;
-    auto kernel = pair_force_kernel<E, S, XPLOR, VIRIAL, NT1>;
+    const size_t smem = Fam::smem_bytes(ntp);
+    auto kernel = row_kernel<Fam>;
     cudaError_t err = ensure_smem(kernel, smem);
     if (err != cudaSuccess)
         return err;
@@ -180,10 +182,10 @@ template<class E, class S> cudaError_t launch_pair(const azp_pair_args* a, const
 template<class E, class S, bool VIRIAL, bool NT1>
 inline cudaError_t launch_dpd_variant(const KernelArgs<S>& k, const void* d_params, const LaunchShape& s, cudaStream_t stream)
     {
-    typedef typename E::cache_type Cache;
+    typedef DpdFamily<E, S, VIRIAL, NT1> Fam;
     const size_t ntp = NT1 ? 1 : size_t(k.ntypes) * k.ntypes;
-    const size_t smem = ntp * sizeof(Cache) + (ntp + 1) * sizeof(S) + 16;
-    auto kernel = dpd_force_kernel<E, S, VIRIAL, NT1>;
+    const size_t smem = Fam::smem_bytes(ntp);
+    auto kernel = row_kernel<Fam>;
     cudaError_t err = ensure_smem(kernel, smem);
     if (err != cudaSuccess)
         return err;
@@ -218,10 +220,10 @@ template<class E, class S> cudaError_t launch_dpd(const azp_pair_args* a, const 
 template<class E, class S, bool VIRIAL, bool NT1>
 inline cudaError_t launch_aniso_variant(const KernelArgs<S>& k, const void* d_params, const LaunchShape& s, cudaStream_t stream)
     {
-    typedef typename E::cache_type Cache;
+    typedef AnisoFamily<E, S, VIRIAL, NT1> Fam;
     const size_t ntp = NT1 ? 1 : size_t(k.ntypes) * k.ntypes;
-    const size_t smem = ntp * sizeof(Cache) + (ntp + 1) * sizeof(S) + 16;
-    auto kernel = aniso_force_kernel<E, S, VIRIAL, NT1>;
+    const size_t smem = Fam::smem_bytes(ntp);
+    auto kernel = row_kernel<Fam>;
     cudaError_t err = ensure_smem(kernel, smem);
     if (err != cudaSuccess)
         return err;

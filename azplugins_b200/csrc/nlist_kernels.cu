@@ -34,6 +34,8 @@ template<class S> struct NlistArgs
     unsigned int* cell_start;
     unsigned int* cell_order;
     CellGrid grid;
+    unsigned int row_offset;
+    unsigned int n_rows;
     };
 
 template<class S> AZP_D void cell_coords(const BoxDim<S>& b, const CellGrid& g, S x, S y, S z, int c[3])
@@ -82,15 +84,16 @@ __global__ void nlist_cell_starts(const unsigned int* sorted_cells, unsigned int
 
 template<class S, bool FILL> __global__ void __launch_bounds__(128) nlist_rows(const NlistArgs<S> a)
     {
-    const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.N)
+    const unsigned int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.n_rows)
         return;
+    const unsigned int i = r + a.row_offset;
     const Vec4<S> pi = load4(a.pos, i);
     const unsigned int ti = scalar_as_uint(pi.w);
     int c[3];
     cell_coords(a.box, a.grid, pi.x, pi.y, pi.z, c);
     unsigned int count = 0;
-    unsigned int* row = FILL ? a.nlist + a.head_list[i] : nullptr;
+    unsigned int* row = FILL ? a.nlist + a.head_list[r] : nullptr;
     for (int oz = -a.grid.reach[2]; oz <= a.grid.reach[2]; ++oz)
         for (int oy = -a.grid.reach[1]; oy <= a.grid.reach[1]; ++oy)
             for (int ox = -a.grid.reach[0]; ox <= a.grid.reach[0]; ++ox)
@@ -135,7 +138,7 @@ template<class S, bool FILL> __global__ void __launch_bounds__(128) nlist_rows(c
                     }
                 }
     if (!FILL)
-        a.n_neigh[i] = count;
+        a.n_neigh[r] = count;
     }
 
 template<class S> static NlistArgs<S> convert(const azp_nlist_args& a)
@@ -161,6 +164,8 @@ template<class S> static NlistArgs<S> convert(const azp_nlist_args& a)
     k.cell_of = a.d_cell_of;
     k.cell_start = a.d_cell_start;
     k.cell_order = a.d_cell_order;
+    k.row_offset = a.n_rows ? a.row_offset : 0u;
+    k.n_rows = a.n_rows ? a.n_rows : a.N;
     return k;
     }
 
@@ -224,8 +229,10 @@ template<class S, bool FILL> static int rows(const azp_nlist_args* a, cudaStream
     if (a->N == 0)
         return 0;
     const NlistArgs<S> k = convert<S>(*a);
+    if ((unsigned long long)k.row_offset + k.n_rows > a->N)
+        return (int)cudaErrorInvalidValue;
     const unsigned int block = 128;
-    nlist_rows<S, FILL><<<(a->N + block - 1) / block, block, 0, st>>>(k);
+    nlist_rows<S, FILL><<<(k.n_rows + block - 1) / block, block, 0, st>>>(k);
     return (int)cudaGetLastError();
     }
     } // namespace azp

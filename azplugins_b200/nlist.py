@@ -105,7 +105,10 @@ class Cell(NeighborList):
         self.deterministic = deterministic
         self.row_align = int(row_align)
 
-    def build(self, state):
+    def build(self, state, rows=None):
+        """Build the list for all particles of ``state`` or, with ``rows=(lo, hi)``, only for the
+        rows of particles [lo, hi) (neighbours are still searched among all particles and stored
+        as global indices; n_neigh / head_list are then indexed by row - lo)."""
         if not state.pos.is_cuda:
             raise _lib.AzpError("nlist.Cell builds on the GPU only (no CPU fallback)")
         bits = 8 * state.dtype.itemsize
@@ -121,6 +124,8 @@ class Cell(NeighborList):
                 raise ValueError("box too small for r_cut + buffer (minimum image)")
         dev = state.device
         n_total = state.pos.shape[0]
+        lo, hi = (0, n_total) if rows is None else (int(rows[0]), int(rows[1]))
+        n_rows = hi - lo
         stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         with torch.cuda.device(dev):
             rl = r_list.astype(state.dtype)
@@ -140,7 +145,9 @@ class Cell(NeighborList):
             cell_of = torch.empty(n_total, dtype=torch.int32, device=dev)
             cell_start = torch.empty(ncells + 1, dtype=torch.int32, device=dev)
             cell_order = torch.empty(n_total, dtype=torch.int32, device=dev)
-            n_neigh = torch.empty(n_total, dtype=torch.int32, device=dev)
+            n_neigh = torch.empty(n_rows, dtype=torch.int32, device=dev)
+            a.row_offset = lo
+            a.n_rows = n_rows
             a.d_cell_of = cell_of.data_ptr()
             a.d_cell_start = cell_start.data_ptr()
             a.d_cell_order = cell_order.data_ptr()
@@ -148,8 +155,8 @@ class Cell(NeighborList):
             _lib.check(getattr(_lib.lib, "azp_nlist_bin" + sfx)(ctypes.byref(a), stream), "nlist bin")
             _lib.check(getattr(_lib.lib, "azp_nlist_count" + sfx)(ctypes.byref(a), stream), "nlist count")
             # head_list = prefix sum of Nmax[type] (HOOMD's row capacity rule)
-            typeid = particle_typeid(state.pos)
-            cap = torch.zeros(n_total, dtype=torch.int64, device=dev)
+            typeid = particle_typeid(state.pos)[lo:hi]
+            cap = torch.zeros(n_rows, dtype=torch.int64, device=dev)
             for t in range(nt):
                 sel = typeid == t
                 if bool(sel.any()):

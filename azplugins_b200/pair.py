@@ -199,7 +199,7 @@ class Pair:
     def _extra_args(self, timestep):
         return {}
 
-    def _args(self, timestep=None, compute_virial=True):
+    def _args(self, timestep=None, compute_virial=True, row_ids=None):
         st = self._state
         if st is None:
             raise RuntimeError("potential is not attached to a State")
@@ -213,11 +213,14 @@ class Pair:
             ntypes=st.ntypes, force=self._force, virial=self._virial if compute_virial else None,
             n_rows=st.N, shift_mode=_lib.SHIFT_MODES[self._mode], compute_virial=compute_virial,
             block_size=self._launch_shape[0], threads_per_particle=self._launch_shape[1],
-            timestep=ts, size_neigh_list=self.nlist.size, **self._extra_args(ts))
+            timestep=ts, size_neigh_list=self.nlist.size, row_ids=row_ids,
+            **self._extra_args(ts))
 
-    def compute(self, timestep=None, compute_virial=True):
-        """``ForceCompute::compute(timestep)``: enqueue the kernel on the current stream."""
-        args = self._args(timestep, compute_virial)
+    def compute(self, timestep=None, compute_virial=True, row_ids=None):
+        """``ForceCompute::compute(timestep)``: enqueue the kernel on the current stream.
+        ``row_ids`` (int32 device tensor) restricts the evaluation to those rows (scheduler use:
+        interior rows while the halo exchange is in flight, boundary rows after)."""
+        args = self._args(timestep, compute_virial, row_ids)
         with torch.cuda.device(self._state.device):
             kernels.launch(self._family, self._evaluator, self._bits, args, self._d_params.data_ptr())
         self._computed = True

@@ -1,0 +1,293 @@
+"""Multi-GPU particle-slice scheduler: one process per GPU, each owning a
+contiguous range of the spatially sorted particles and the neighbour-list rows of that range.
+
+With a full neighbour list every row is independent and writes only its own outputs, so the path
+shards by rows with no reduction. What a rank needs from its peers are the positions (and
+velocities / orientations) of the particles its rows reference but it does not own -- its
+*ghosts*, exactly HOOMD's domain-decomposition picture (rows [0, N) local, indices >= N ghosts,
+SURVEY.md Appendix A.2). Per step:
+
+    1. pack the locally owned particles each peer asked for            (comm stream)
+    2. exchange them point-to-point over NCCL / NVLink                 (comm stream)
+    3. meanwhile evaluate the INTERIOR rows -- rows without ghosts --  (compute stream)
+    4. when the halo has landed, evaluate the BOUNDARY rows            (compute stream)
+
+The plan (who owns what, ghost lists, index remapping, interior/boundary split) is pure index
+logic on torch tensors and runs on any device/backend; it is built once per neighbour-list
+build. Only the force evaluation needs CUDA.
+"""
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def partition_bounds(n_total, world):
+    """Row bounds of ``world`` contiguous slices with near-equal particle counts (int64[world+1]).
+    (Rows of the BASELINE fluids have near-equal length; for skewed rows pass weights.)"""
+    return np.array([(n_total * r) // world for r in range(world + 1)], dtype=np.int64)
+
+
+def partition_bounds_weighted(weights, world):
+    """Bounds balancing the sum of ``weights`` (e.g. n_neigh) instead of the particle count."""
+    w = np.asarray(weights, dtype=np.float64)
+    c = np.concatenate([[0.0], np.cumsum(w)])
+    targets = c[-1] * np.arange(world + 1) / world
+    b = np.searchsorted(c, targets, side="left")
+    b[0], b[-1] = 0, len(w)
+    return np.maximum.accumulate(b).astype(np.int64)
+
+
+class SlicePlan:
+    """Index plan of one rank: ghosts, remapped neighbour list, exchange lists, row classes."""
+
+    def __init__(self, rank, world, bounds, n_neigh, head_list, nlist_global):
+        """``n_neigh`` / ``head_list`` / ``nlist_global``: rows of particles [lo, hi) with GLOBAL
+        neighbour indices (torch tensors, any device)."""
+        self.rank, self.world = rank, world
+        self.bounds = np.asarray(bounds, dtype=np.int64)
+        lo, hi = int(self.bounds[rank]), int(self.bounds[rank + 1])
+        self.lo, self.hi, self.n_local = lo, hi, hi - lo
+        dev = nlist_global.device
+        nn = n_neigh.to(torch.int64)
+        head = head_list.to(torch.int64)
+        size = int(nlist_global.numel())
+        # row of every stored entry and whether the entry is valid (k < n_neigh[row])
+        cap = torch.diff(head, append=torch.tensor([size], dtype=torch.int64, device=dev))
+        row_of = torch.repeat_interleave(torch.arange(self.n_local, device=dev), cap,
+                                         output_size=size)
+        k = torch.arange(size, device=dev) - head[row_of]
+        valid = k < nn[row_of]
+        j = nlist_global.to(torch.int64) & 0xFFFFFFFF
+        own = (j >= lo) & (j < hi)
+        ghost_entry = valid & ~own
+        self.ghost_ids = torch.unique(j[ghost_entry])  # sorted global ids
+        self.n_ghost = int(self.ghost_ids.numel())
+        # local index: own -> j - lo; ghost -> n_local + rank in ghost_ids; padding -> 0
+        gpos = torch.searchsorted(self.ghost_ids, j.clamp(min=0)) if self.n_ghost else torch.zeros_like(j)
+        j_local = torch.where(own, j - lo, self.n_local + gpos)
+        j_local = torch.where(valid, j_local, torch.zeros_like(j_local))
+        self.nlist_local = j_local.to(torch.int32)
+        self.n_neigh = n_neigh
+        self.head_list = head_list
+        # interior rows have no ghost entry
+        has_ghost = torch.zeros(self.n_local, dtype=torch.bool, device=dev)
+        has_ghost[row_of[ghost_entry]] = True
+        rows = torch.arange(self.n_local, dtype=torch.int32, device=dev)
+        self.interior_rows = rows[~has_ghost].contiguous()
+        self.boundary_rows = rows[has_ghost].contiguous()
+        # owner of each ghost (owners are contiguous ranges -> segments of the sorted id list)
+        b = torch.from_numpy(self.bounds).to(dev)
+        owner = torch.searchsorted(b, self.ghost_ids, right=True) - 1
+        self.recv_counts = torch.bincount(owner, minlength=world).cpu().numpy().astype(np.int64)
+        self.recv_offsets = np.concatenate([[0], np.cumsum(self.recv_counts)])[:-1]
+        self.send_idx = None  # filled by negotiate()
+
+    def negotiate(self, group=None):
+        """Tell every owner which of its particles this rank needs; learn what to send."""
+        wanted = []
+        ids = self.ghost_ids.cpu().numpy()
+        for r in range(self.world):
+            o, c = int(self.recv_offsets[r]), int(self.recv_counts[r])
+            wanted.append(ids[o:o + c])
+        if self.world == 1:
+            self.send_idx = [torch.zeros(0, dtype=torch.int64, device=self.ghost_ids.device)]
+            return self
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, wanted, group=group)
+        dev = self.ghost_ids.device
+        self.send_idx = []
+        for r in range(self.world):
+            need = np.asarray(gathered[r][self.rank], dtype=np.int64)  # global ids rank r wants from me
+            assert need.size == 0 or (need.min() >= self.lo and need.max() < self.hi)
+            self.send_idx.append(torch.from_numpy(need - self.lo).to(dev))
+        self.send_counts = np.array([int(s.numel()) for s in self.send_idx], dtype=np.int64)
+        return self
+
+
+class HaloExchange:
+    """Per-step exchange of one or more Scalar4 arrays laid out [local | ghosts]."""
+
+    def __init__(self, plan, group=None):
+        self.plan = plan
+        self.group = group
+        self.peers = [r for r in range(plan.world) if r != plan.rank
+                      and (plan.recv_counts[r] > 0 or plan.send_counts[r] > 0)] if plan.world > 1 else []
+        self._send_cat = torch.cat([plan.send_idx[r] for r in self.peers]) if self.peers else None
+        self._send_off = np.concatenate([[0], np.cumsum([plan.send_counts[r] for r in self.peers])]) \
+            if self.peers else None
+        self._buf = {}
+
+    def bytes_per_step(self, arrays):
+        n = sum(int(self.plan.recv_counts[r]) for r in self.peers)
+        return sum(n * a.shape[1] * a.element_size() for a in arrays)
+
+    def __call__(self, arrays):
+        """Update the ghost region of every array in ``arrays`` from the owners (in place)."""
+        if not self.peers:
+            return
+        p = self.plan
+        ops, keep = [], []
+        for ai, a in enumerate(arrays):
+            key = (ai, a.dtype, a.shape[1])
+            nsend = int(self._send_off[-1])
+            if key not in self._buf or self._buf[key].shape[0] != nsend:
+                self._buf[key] = torch.empty((nsend, a.shape[1]), dtype=a.dtype, device=a.device)
+            sbuf = self._buf[key]
+            torch.index_select(a[:p.n_local], 0, self._send_cat, out=sbuf)  # pack
+            for pi_, r in enumerate(self.peers):
+                s0, s1 = int(self._send_off[pi_]), int(self._send_off[pi_ + 1])
+                if s1 > s0:
+                    ops.append(dist.P2POp(dist.isend, sbuf[s0:s1], r, group=self.group))
+                c = int(p.recv_counts[r])
+                if c:
+                    o = p.n_local + int(p.recv_offsets[r])
+                    ops.append(dist.P2POp(dist.irecv, a[o:o + c], r, group=self.group))
+            keep.append(sbuf)
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+
+class SliceScheduler:
+    """One rank's slice of a workload: local+ghost State, remapped list, potentials, exchange."""
+
+    def __init__(self, plan, state, nlist, pots, exchange_arrays, group=None):
+        self.plan = plan
+        self.state = state
+        self.nlist = nlist
+        self.pots = pots
+        self.exchange_arrays = exchange_arrays
+        self.halo = HaloExchange(plan, group)
+        self.n_local = plan.n_local
+        self.comm_stream = torch.cuda.Stream(device=state.device)
+        self._halo_done = torch.cuda.Event()
+        self._step_done = torch.cuda.Event()
+        self._step_done.record()
+        self.launches_per_step = len(pots) * ((1 if plan.interior_rows.numel() else 0)
+                                              + (1 if plan.boundary_rows.numel() else 0))
+        self._host = None
+
+    # ---- construction from a synthetic workload ------------------------------------------
+    @classmethod
+    def from_workload(cls, wl, rank, world, device, dtype=np.float32, buffer=0.4, group=None):
+        """Every rank generates the same global workload (seeded), builds the rows of its slice
+        on its GPU, derives the plan and keeps only local + ghost particles."""
+        from . import nlist as aznlist
+        from .state import State
+
+        bounds = partition_bounds(wl.N, world)
+        lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+        g = wl.make_state(dtype=dtype, device=device)  # global arrays, setup only
+        cell = aznlist.Cell(buffer=buffer)
+        probe = wl.make_potentials(cell)  # registers the cutoffs with the list
+        cell.build(g, rows=(lo, hi))
+        plan = SlicePlan(rank, world, bounds, cell.n_neigh, cell.head_list, cell.nlist)
+        plan.negotiate(group)
+        ids = torch.cat([torch.arange(lo, hi, device=g.pos.device), plan.ghost_ids])
+        state = State.__new__(State)
+        state.box, state.types, state.dtype, state.device = g.box, g.types, g.dtype, g.device
+        state.seed, state.timestep, state.dt = g.seed, g.timestep, g.dt
+        state.N, state.n_ghost = plan.n_local, plan.n_ghost
+        state.pos = g.pos[ids].contiguous()
+        state.vel = g.vel[ids].contiguous()
+        state.orientation = g.orientation[ids].contiguous()
+        state.tag = g.tag[ids].contiguous()
+        local_list = aznlist.NeighborList.from_arrays(plan.n_neigh, plan.nlist_local,
+                                                      plan.head_list, device=device, buffer=buffer)
+        del g, cell, probe
+        torch.cuda.empty_cache()
+        pots = wl.make_potentials(local_list)
+        for p in pots:
+            p.attach(state)
+        arrays = [state.pos]
+        names = {type(p).__name__ for p in pots}
+        if "DPDGeneralWeight" in names:
+            arrays.append(state.vel)
+        if "TwoPatchMorse" in names:
+            arrays.append(state.orientation)
+        return cls(plan, state, local_list, pots, arrays, group)
+
+    # ---- per step ------------------------------------------------------------------------
+    def exchange_bytes_per_step(self):
+        return self.halo.bytes_per_step(self.exchange_arrays)
+
+    def mean_row_length(self):
+        return float(self.nlist.n_neigh.double().mean().item())
+
+    def step(self, compute_virial=False):
+        p = self.plan
+        cur = torch.cuda.current_stream()
+        # the exchange may overwrite ghosts only after the previous step's boundary rows are done
+        self.comm_stream.wait_event(self._step_done)
+        with torch.cuda.stream(self.comm_stream):
+            self.halo(self.exchange_arrays)
+            self._halo_done.record()
+        if p.interior_rows.numel():
+            for pot in self.pots:
+                pot.compute(compute_virial=compute_virial, row_ids=p.interior_rows)
+        cur.wait_event(self._halo_done)
+        if p.boundary_rows.numel():
+            for pot in self.pots:
+                pot.compute(compute_virial=compute_virial, row_ids=p.boundary_rows)
+        self._step_done.record()
+
+    def tune(self, compute_virial=False):
+        """Autotune each potential's launch shape on the interior rows."""
+        out = []
+        self.halo(self.exchange_arrays)
+        torch.cuda.synchronize()
+        for pot in self.pots:
+            pot.nlist.check_dist = False
+            args = pot._args(None, compute_virial, self.plan.interior_rows
+                             if self.plan.interior_rows.numel() else None)
+            from . import kernels
+
+            b, t, ms = kernels.autotune(pot._family, pot._evaluator, pot._bits, args,
+                                        pot._d_params.data_ptr())
+            pot.kernel_parameters = (b, t)
+            out.append((b, t, ms))
+        return out
+
+    def time_kernels(self, steps, compute_virial=False):
+        """ms per step of the force kernels alone (no exchange), CUDA events."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            for rows in (self.plan.interior_rows, self.plan.boundary_rows):
+                if rows.numel():
+                    for pot in self.pots:
+                        pot.compute(compute_virial=compute_virial, row_ids=rows)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    # ---- end to end with host buffers -------------------------------------------------------
+    def _host_buffers(self, compute_virial):
+        if self._host is None:
+            st = self.state
+            self._host = dict(
+                pos=torch.empty((self.n_local, 4), dtype=st.pos.dtype).pin_memory(),
+                force=torch.empty_like(self.pots[0]._force, device="cpu").pin_memory(),
+                virial=torch.empty_like(self.pots[0]._virial, device="cpu").pin_memory())
+            self._host["pos"].copy_(st.pos[:self.n_local])
+        return self._host
+
+    def e2e_bytes(self, compute_virial):
+        h = self._host_buffers(compute_virial)
+        h2d = h["pos"].numel() * h["pos"].element_size()
+        d2h = h["force"].numel() * h["force"].element_size() * len(self.pots)
+        if compute_virial:
+            d2h += h["virial"].numel() * h["virial"].element_size() * len(self.pots)
+        return h2d, d2h
+
+    def e2e_step(self, compute_virial=False):
+        h = self._host_buffers(compute_virial)
+        self.state.pos[:self.n_local].copy_(h["pos"], non_blocking=True)
+        self._step_done.record()
+        self.step(compute_virial)
+        for pot in self.pots:
+            h["force"].copy_(pot._force, non_blocking=True)
+            if compute_virial:
+                h["virial"].copy_(pot._virial, non_blocking=True)
+        torch.cuda.current_stream().synchronize()

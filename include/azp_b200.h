@@ -184,6 +184,11 @@ typedef struct azp_nlist_args
     uint32_t* d_cell_start;      /* [ncells + 1] scratch */
     uint32_t* d_cell_order;      /* [N] scratch */
     uint32_t cell_dim[3];        /* from azp_nlist_cell_dim */
+    /* rows to build: particles [row_offset, row_offset + n_rows) against all N particles;
+     * d_n_neigh / d_head_list are indexed by row - row_offset. n_rows = 0 means all N rows.
+     * (Used by the multi-GPU scheduler: a rank builds only the rows of its particle slice.) */
+    uint32_t row_offset;
+    uint32_t n_rows;
     uint32_t _pad;
     } azp_nlist_args;
 
