@@ -7,6 +7,11 @@ the shared object is missing the import fails loudly and tells the user how to b
 import ctypes
 import os
 
+# libazp_b200.so links the shared CUDA runtime. Import torch first so that the libcudart already
+# mapped by torch is the one the library binds to (one runtime instance: same current device,
+# same streams).
+import torch  # noqa: F401
+
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libazp_b200.so")
 

@@ -122,19 +122,15 @@ class HaloExchange:
         n = sum(int(self.plan.recv_counts[r]) for r in self.peers)
         return sum(n * a.shape[1] * a.element_size() for a in arrays)
 
-    def __call__(self, arrays):
-        """Update the ghost region of every array in ``arrays`` from the owners (in place)."""
-        if not self.peers:
-            return
+    def _plan_ops(self, arrays):
+        """Point-to-point descriptors for `arrays` (buffers are persistent, so the list is built
+        once and re-posted every step)."""
         p = self.plan
-        ops, keep = [], []
-        for ai, a in enumerate(arrays):
-            key = (ai, a.dtype, a.shape[1])
-            nsend = int(self._send_off[-1])
-            if key not in self._buf or self._buf[key].shape[0] != nsend:
-                self._buf[key] = torch.empty((nsend, a.shape[1]), dtype=a.dtype, device=a.device)
-            sbuf = self._buf[key]
-            torch.index_select(a[:p.n_local], 0, self._send_cat, out=sbuf)  # pack
+        ops, packs = [], []
+        nsend = int(self._send_off[-1])
+        for a in arrays:
+            sbuf = torch.empty((nsend, a.shape[1]), dtype=a.dtype, device=a.device)
+            packs.append((a, sbuf))
             for pi_, r in enumerate(self.peers):
                 s0, s1 = int(self._send_off[pi_]), int(self._send_off[pi_ + 1])
                 if s1 > s0:
@@ -143,7 +139,20 @@ class HaloExchange:
                 if c:
                     o = p.n_local + int(p.recv_offsets[r])
                     ops.append(dist.P2POp(dist.irecv, a[o:o + c], r, group=self.group))
-            keep.append(sbuf)
+        return ops, packs
+
+    def __call__(self, arrays):
+        """Update the ghost region of every array in ``arrays`` from the owners (in place)."""
+        if not self.peers:
+            return
+        key = tuple(a.data_ptr() for a in arrays)
+        if key not in self._buf:
+            self._buf.clear()
+            self._buf[key] = self._plan_ops(arrays)
+        ops, packs = self._buf[key]
+        n_local = self.plan.n_local
+        for a, sbuf in packs:
+            torch.index_select(a[:n_local], 0, self._send_cat, out=sbuf)  # pack
         for req in dist.batch_isend_irecv(ops):
             req.wait()
 
@@ -219,12 +228,13 @@ class SliceScheduler:
         cur = torch.cuda.current_stream()
         # the exchange may overwrite ghosts only after the previous step's boundary rows are done
         self.comm_stream.wait_event(self._step_done)
-        with torch.cuda.stream(self.comm_stream):
-            self.halo(self.exchange_arrays)
-            self._halo_done.record()
+        # interior rows first: they are already running while the host posts the exchange
         if p.interior_rows.numel():
             for pot in self.pots:
                 pot.compute(compute_virial=compute_virial, row_ids=p.interior_rows)
+        with torch.cuda.stream(self.comm_stream):
+            self.halo(self.exchange_arrays)
+            self._halo_done.record()
         cur.wait_event(self._halo_done)
         if p.boundary_rows.numel():
             for pot in self.pots:
