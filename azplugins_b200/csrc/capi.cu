@@ -306,6 +306,8 @@ extern "C"
                 azp_pair_args t = *a;
                 t.block_size = blocks[bi];
                 t.threads_per_particle = tpp;
+                if (bits == 64 && blocks[bi] > 256)
+                    continue; // fp64 kernels are built for blocks of at most 256 threads
                 rc = run_family(family, ev, bits, &t, p, st); // warm-up
                 if (rc != 0)
                     break;

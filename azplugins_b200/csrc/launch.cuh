@@ -74,10 +74,10 @@ inline bool is_pow2(unsigned int x)
 // Launch parameters: honour the caller's (block_size, threads_per_particle) -- HOOMD's autotuner
 // dimensions -- or choose from the mean row capacity: about 12-16 neighbours per lane keeps the
 // tail waste of a row under 5 % while leaving enough rows per warp for coalesced outputs.
-inline cudaError_t choose_shape(const azp_pair_args& a, LaunchShape& s)
+inline cudaError_t choose_shape(const azp_pair_args& a, LaunchShape& s, unsigned int block_limit)
     {
     unsigned int block = a.block_size ? a.block_size : 128u;
-    if (block % 32u != 0 || block > kMaxBlock)
+    if (block % 32u != 0 || block > block_limit)
         return cudaErrorInvalidValue;
     unsigned int tpp = a.threads_per_particle;
     if (tpp == 0)
@@ -135,11 +135,11 @@ template<class K> inline cudaError_t ensure_smem(K kernel, size_t bytes)
     return cudaSuccess;
     }
 
-template<class E, class S, bool XPLOR, bool VIRIAL, bool NT1>
+template<class E, class S, bool XPLOR, bool VIRIAL, int NTM>
 inline cudaError_t launch_pair_variant(const KernelArgs<S>& k, const void* d_params, const LaunchShape& s, cudaStream_t stream)
     {
-    typedef IsoFamily<E, S, XPLOR, VIRIAL, NT1> Fam;
-    const size_t ntp = NT1 ? 1 : size_t(k.ntypes) * k.ntypes;
+    typedef IsoFamily<E, S, XPLOR, VIRIAL, NTM> Fam;
+    const size_t ntp = NTM == 1 ? 1 : size_t(k.ntypes) * k.ntypes;
     const size_t smem = Fam::smem_bytes(ntp);
     auto kernel = row_kernel<Fam>;
     cudaError_t err = ensure_smem(kernel, smem);
@@ -159,31 +159,36 @@ template<class E, class S> cudaError_t launch_pair(const azp_pair_args* a, const
     if (nothing_to_do(a))
         return cudaSuccess;
     LaunchShape s;
-    err = choose_shape(*a, s);
+    err = choose_shape(*a, s, max_block<S>());
     if (err != cudaSuccess)
         return err;
     const KernelArgs<S> k = convert_args<S>(*a);
-    const bool xplor = a->shift_mode == 2, vir = a->compute_virial != 0, nt1 = a->ntypes == 1;
+    const bool xplor = a->shift_mode == 2, vir = a->compute_virial != 0;
+    const int ntm = a->ntypes == 1 ? 1 : (a->ntypes == 2 ? 2 : 0);
 #define AZP_CASE(X, V, T)           \
-    if (xplor == X && vir == V && nt1 == T) \
+    if (xplor == X && vir == V && ntm == T) \
         return launch_pair_variant<E, S, X, V, T>(k, d_params, s, stream);
-    AZP_CASE(false, false, false)
-    AZP_CASE(false, false, true)
-    AZP_CASE(false, true, false)
-    AZP_CASE(false, true, true)
-    AZP_CASE(true, false, false)
-    AZP_CASE(true, false, true)
-    AZP_CASE(true, true, false)
-    AZP_CASE(true, true, true)
+    AZP_CASE(false, false, 0)
+    AZP_CASE(false, false, 1)
+    AZP_CASE(false, false, 2)
+    AZP_CASE(false, true, 0)
+    AZP_CASE(false, true, 1)
+    AZP_CASE(false, true, 2)
+    AZP_CASE(true, false, 0)
+    AZP_CASE(true, false, 1)
+    AZP_CASE(true, false, 2)
+    AZP_CASE(true, true, 0)
+    AZP_CASE(true, true, 1)
+    AZP_CASE(true, true, 2)
 #undef AZP_CASE
     return cudaErrorInvalidValue;
     }
 
-template<class E, class S, bool VIRIAL, bool NT1>
+template<class E, class S, bool VIRIAL, int NTM>
 inline cudaError_t launch_dpd_variant(const KernelArgs<S>& k, const void* d_params, const LaunchShape& s, cudaStream_t stream)
     {
-    typedef DpdFamily<E, S, VIRIAL, NT1> Fam;
-    const size_t ntp = NT1 ? 1 : size_t(k.ntypes) * k.ntypes;
+    typedef DpdFamily<E, S, VIRIAL, NTM> Fam;
+    const size_t ntp = NTM == 1 ? 1 : size_t(k.ntypes) * k.ntypes;
     const size_t smem = Fam::smem_bytes(ntp);
     auto kernel = row_kernel<Fam>;
     cudaError_t err = ensure_smem(kernel, smem);
@@ -203,25 +208,32 @@ template<class E, class S> cudaError_t launch_dpd(const azp_pair_args* a, const 
     if (!a->d_vel || !a->d_tag)
         return cudaErrorInvalidValue;
     LaunchShape s;
-    err = choose_shape(*a, s);
+    err = choose_shape(*a, s, max_block<S>());
     if (err != cudaSuccess)
         return err;
     const KernelArgs<S> k = convert_args<S>(*a);
-    const bool vir = a->compute_virial != 0, nt1 = a->ntypes == 1;
-    if (vir && nt1)
-        return launch_dpd_variant<E, S, true, true>(k, d_params, s, stream);
+    const bool vir = a->compute_virial != 0;
+    const int ntm = a->ntypes == 1 ? 1 : (a->ntypes == 2 ? 2 : 0);
     if (vir)
-        return launch_dpd_variant<E, S, true, false>(k, d_params, s, stream);
-    if (nt1)
-        return launch_dpd_variant<E, S, false, true>(k, d_params, s, stream);
-    return launch_dpd_variant<E, S, false, false>(k, d_params, s, stream);
+        {
+        if (ntm == 1)
+            return launch_dpd_variant<E, S, true, 1>(k, d_params, s, stream);
+        if (ntm == 2)
+            return launch_dpd_variant<E, S, true, 2>(k, d_params, s, stream);
+        return launch_dpd_variant<E, S, true, 0>(k, d_params, s, stream);
+        }
+    if (ntm == 1)
+        return launch_dpd_variant<E, S, false, 1>(k, d_params, s, stream);
+    if (ntm == 2)
+        return launch_dpd_variant<E, S, false, 2>(k, d_params, s, stream);
+    return launch_dpd_variant<E, S, false, 0>(k, d_params, s, stream);
     }
 
-template<class E, class S, bool VIRIAL, bool NT1>
+template<class E, class S, bool VIRIAL, int NTM>
 inline cudaError_t launch_aniso_variant(const KernelArgs<S>& k, const void* d_params, const LaunchShape& s, cudaStream_t stream)
     {
-    typedef AnisoFamily<E, S, VIRIAL, NT1> Fam;
-    const size_t ntp = NT1 ? 1 : size_t(k.ntypes) * k.ntypes;
+    typedef AnisoFamily<E, S, VIRIAL, NTM> Fam;
+    const size_t ntp = NTM == 1 ? 1 : size_t(k.ntypes) * k.ntypes;
     const size_t smem = Fam::smem_bytes(ntp);
     auto kernel = row_kernel<Fam>;
     cudaError_t err = ensure_smem(kernel, smem);
@@ -243,18 +255,25 @@ template<class E, class S> cudaError_t launch_aniso(const azp_pair_args* a, cons
     if (!a->d_orientation || !a->d_torque)
         return cudaErrorInvalidValue;
     LaunchShape s;
-    err = choose_shape(*a, s);
+    err = choose_shape(*a, s, max_block<S>());
     if (err != cudaSuccess)
         return err;
     const KernelArgs<S> k = convert_args<S>(*a);
-    const bool vir = a->compute_virial != 0, nt1 = a->ntypes == 1;
-    if (vir && nt1)
-        return launch_aniso_variant<E, S, true, true>(k, d_params, s, stream);
+    const bool vir = a->compute_virial != 0;
+    const int ntm = a->ntypes == 1 ? 1 : (a->ntypes == 2 ? 2 : 0);
     if (vir)
-        return launch_aniso_variant<E, S, true, false>(k, d_params, s, stream);
-    if (nt1)
-        return launch_aniso_variant<E, S, false, true>(k, d_params, s, stream);
-    return launch_aniso_variant<E, S, false, false>(k, d_params, s, stream);
+        {
+        if (ntm == 1)
+            return launch_aniso_variant<E, S, true, 1>(k, d_params, s, stream);
+        if (ntm == 2)
+            return launch_aniso_variant<E, S, true, 2>(k, d_params, s, stream);
+        return launch_aniso_variant<E, S, true, 0>(k, d_params, s, stream);
+        }
+    if (ntm == 1)
+        return launch_aniso_variant<E, S, false, 1>(k, d_params, s, stream);
+    if (ntm == 2)
+        return launch_aniso_variant<E, S, false, 2>(k, d_params, s, stream);
+    return launch_aniso_variant<E, S, false, 0>(k, d_params, s, stream);
     }
     } // namespace azp
 

@@ -18,8 +18,8 @@
 //   * per type-pair constants (Evaluator::cache_type: parameters, derived constants, energy at
 //     r_cut) and the effective r_cut^2 are built once per CTA in shared memory; a pair whose
 //     potential is switched off gets r_cut^2 = 0, so ONE compare per neighbour implements the
-//     reference's "rsq < rcutsq && parameter != 0" test. Single-type systems (NT1) keep the
-//     constants in registers;
+//     reference's "rsq < rcutsq && parameter != 0" test. Single-type systems keep the constants
+//     in registers for the whole kernel, two-type systems per row (TypeLookup, NTM = 1 / 2 / 0);
 //   * minimum image costs 3 full-rate instructions per axis (magic-number rint, no FRND) and is
 //     skipped for a whole warp when every row of the warp is farther than the largest cutoff
 //     from all periodic faces: for such rows wrapping can only change pairs that fail the
@@ -64,7 +64,14 @@ template<class S> struct KernelArgs
     S T;
     };
 
+// largest block_size accepted: 512 threads (<= 128 registers) for fp32; the fp64 variants hold
+// twice the register state (software pipeline + accumulators), so they are compiled for blocks of
+// at most 256 threads (<= 255 registers) instead of spilling.
 constexpr unsigned int kMaxBlock = 512;
+template<class S> constexpr unsigned int max_block()
+    {
+    return sizeof(S) == 8 ? 256u : kMaxBlock;
+    }
 
 template<class S> AZP_D S shfl_xor(S v, unsigned int o)
     {
@@ -172,20 +179,96 @@ template<class E, class S> struct PairTable
         }
     };
 
+// Word-wise select between two POD structs held in registers (compiles to one SEL per live word).
+template<class C> AZP_D C select_words(bool pick_b, const C& a, const C& b)
+    {
+    static_assert(sizeof(C) % 4 == 0, "cache_type must be a multiple of 4 bytes");
+    union U
+        {
+        C c;
+        uint32_t w[sizeof(C) / 4];
+        AZP_D U() { }
+        };
+    U ua, ub, uo;
+    ua.c = a;
+    ub.c = b;
+#pragma unroll
+    for (unsigned int k = 0; k < sizeof(C) / 4; ++k)
+        uo.w[k] = pick_b ? ub.w[k] : ua.w[k];
+    return uo.c;
+    }
+
+// How a family finds the constants of the (type_i, type_j) pair of a neighbour. NTM is the
+// "type mode" template flag of the kernels:
+//   1  single-type system: one set of constants, in registers for the whole kernel;
+//   2  two types: the two candidate sets of the row (type_j = 0 / 1 given type_i) are loaded into
+//      registers once per row and a neighbour picks one with a predicate select -- no shared
+//      memory traffic in the neighbour loop (the L1/LSU data pipe is this kernel's scarce
+//      resource);
+//   0  general: tables in shared memory, indexed per neighbour with Index2D.
+template<class E, class S, int NTM> struct TypeLookup
+    {
+    typedef typename E::cache_type Cache;
+    PairTable<E, S> tab;
+    Cache cA, cB;
+    S rcA, rcB;
+    unsigned int ti, ntypes;
+
+    AZP_D void after_stage()
+        {
+        if (NTM == 1)
+            {
+            cA = tab.cache(0);
+            rcA = tab.rcutsq(0);
+            }
+        }
+    AZP_D void begin_row(unsigned int ti_, unsigned int ntypes_)
+        {
+        ti = ti_;
+        ntypes = ntypes_;
+        if (NTM == 2)
+            {
+            const unsigned int t = ti_ & 1u; // defensive: ids outside {0,1} cannot index past the table
+            cA = tab.cache(index2d(2u, t, 0u));
+            cB = tab.cache(index2d(2u, t, 1u));
+            rcA = tab.rcutsq(index2d(2u, t, 0u));
+            rcB = tab.rcutsq(index2d(2u, t, 1u));
+            }
+        }
+    AZP_D unsigned int pair_index(unsigned int tj) const
+        {
+        return NTM == 1 ? 0u : index2d(NTM == 2 ? 2u : ntypes, ti, tj);
+        }
+    AZP_D S rcutsq(unsigned int tj) const
+        {
+        if (NTM == 1)
+            return rcA;
+        if (NTM == 2)
+            return tj ? rcB : rcA;
+        return tab.rcutsq(index2d(ntypes, ti, tj));
+        }
+    AZP_D Cache cache(unsigned int tj) const
+        {
+        if (NTM == 1)
+            return cA;
+        if (NTM == 2)
+            return select_words(tj != 0u, cA, cB);
+        return tab.cache(index2d(ntypes, ti, tj));
+        }
+    };
+
 // =============================================================================================
 // Isotropic family: F_i = sum dx * force_divr, E_i = 1/2 sum U, W_i = 1/2 sum dx_a dx_b force_divr
 // =============================================================================================
-template<class E_, class S_, bool XPLOR, bool VIRIAL, bool NT1_> struct IsoFamily
+template<class E_, class S_, bool XPLOR, bool VIRIAL, int NTM_> struct IsoFamily
     {
     typedef E_ E;
     typedef S_ S;
     typedef typename E::cache_type Cache;
-    static constexpr bool NT1 = NT1_;
+    static constexpr int NTM = NTM_;
 
-    PairTable<E, S> tab;
+    TypeLookup<E, S, NTM> types;
     unsigned int xplor_off;
-    Cache c0;
-    S rc0;
     S fx = S(0), fy = S(0), fz = S(0), pe = S(0);
     Virial6<S> w;
 
@@ -201,6 +284,7 @@ template<class E_, class S_, bool XPLOR, bool VIRIAL, bool NT1_> struct IsoFamil
 
     AZP_D void stage(const KernelArgs<S>& a, const typename E::param_type* params, unsigned int ntp)
         {
+        PairTable<E, S>& tab = types.tab;
         tab.carve(ntp);
         xplor_off = (tab.end_off(ntp) + 15u) & ~15u;
         for (unsigned int t = threadIdx.x; t < ntp; t += blockDim.x)
@@ -223,30 +307,55 @@ template<class E_, class S_, bool XPLOR, bool VIRIAL, bool NT1_> struct IsoFamil
         __syncthreads();
         tab.finish(ntp);
         __syncthreads();
-        c0 = tab.cache(0);
-        rc0 = tab.rcutsq(0);
+        types.after_stage();
         }
 
-    AZP_D void begin_row(const KernelArgs<S>&, unsigned int) { }
-
-    template<class C>
-    AZP_D void accept(const C& c, unsigned int tp, S rsq, S rcutsq, S dx, S dy, S dz)
+    AZP_D void begin_row(const KernelArgs<S>& a, unsigned int, unsigned int ti)
         {
+        types.begin_row(ti, a.ntypes);
+        }
+
+    AZP_D void pair(const KernelArgs<S>& a, const RowGeometry<S>& g, unsigned int, const Vec4<S>& pj)
+        {
+        S dx, dy, dz;
+        g.displacement(a.box, pj, dx, dy, dz);
+        const S rsq = fma(dz, dz, fma(dy, dy, dx * dx));
+        const unsigned int tj = NTM == 1 ? 0u : scalar_as_uint(pj.w);
+        const S rcutsq = types.rcutsq(tj);
+        const bool inside = rsq < rcutsq;
         S force_divr = S(0), pair_eng = S(0);
-        E eval(rsq, rcutsq, c);
-        eval.evalPair(force_divr, pair_eng, false);
         if (XPLOR)
             {
-            const XplorEntry<S> x = xplor(tp);
-            if (rsq >= x.ronsq)
+            // rare mode: keep the branch (the smoothing reads another table)
+            if (inside)
                 {
-                const S m = rsq - rcutsq;
-                const S s = m * m * (rcutsq + S(2.0) * rsq - S(3.0) * x.ronsq) * x.denom_inv;
-                const S ds = S(12.0) * (rsq - x.ronsq) * m * x.denom_inv;
-                const S old_eng = pair_eng;
-                pair_eng = old_eng * s;
-                force_divr = s * force_divr - ds * old_eng;
+                const Cache c = types.cache(tj);
+                E eval(rsq, rcutsq, c);
+                eval.evalPair(force_divr, pair_eng, false);
+                const XplorEntry<S> x = xplor(types.pair_index(tj));
+                if (rsq >= x.ronsq)
+                    {
+                    const S m = rsq - rcutsq;
+                    const S s = m * m * (rcutsq + S(2.0) * rsq - S(3.0) * x.ronsq) * x.denom_inv;
+                    const S ds = S(12.0) * (rsq - x.ronsq) * m * x.denom_inv;
+                    const S old_eng = pair_eng;
+                    pair_eng = old_eng * s;
+                    force_divr = s * force_divr - ds * old_eng;
+                    }
                 }
+            }
+        else
+            {
+            // Branch-free: in a 32-lane warp some neighbour is always inside the cutoff, so a
+            // branch around the evaluator is never skipped and only costs BSSY/BRA/BSYNC. Every
+            // lane evaluates; rejected lanes are zeroed by a select (which also discards any
+            // inf/NaN the evaluator produced for an out-of-range rsq).
+            const Cache c = types.cache(tj);
+            S f = S(0), e = S(0);
+            E eval(rsq, rcutsq, c);
+            eval.evalPair(f, e, false);
+            force_divr = inside ? f : S(0);
+            pair_eng = inside ? e : S(0);
             }
         fx = fma(dx, force_divr, fx);
         fy = fma(dy, force_divr, fy);
@@ -261,25 +370,6 @@ template<class E_, class S_, bool XPLOR, bool VIRIAL, bool NT1_> struct IsoFamil
             w.yy = fma(dy, vy, w.yy);
             w.yz = fma(dy, vz, w.yz);
             w.zz = fma(dz, vz, w.zz);
-            }
-        }
-
-    AZP_D void pair(const KernelArgs<S>& a, const RowGeometry<S>& g, unsigned int, const Vec4<S>& pj)
-        {
-        S dx, dy, dz;
-        g.displacement(a.box, pj, dx, dy, dz);
-        const S rsq = fma(dz, dz, fma(dy, dy, dx * dx));
-        if (NT1)
-            {
-            if (rsq < rc0)
-                accept(c0, 0u, rsq, rc0, dx, dy, dz);
-            }
-        else
-            {
-            const unsigned int tp = index2d(a.ntypes, g.ti, scalar_as_uint(pj.w));
-            const S rcutsq = tab.rcutsq(tp);
-            if (rsq < rcutsq)
-                accept(tab.cache(tp), tp, rsq, rcutsq, dx, dy, dz);
             }
         }
 
@@ -307,16 +397,14 @@ template<class E_, class S_, bool XPLOR, bool VIRIAL, bool NT1_> struct IsoFamil
 // DPD thermostat family: also gathers vel_j and tag_j; force from force_divr (conservative +
 // drag + random), virial from the conservative part only.
 // =============================================================================================
-template<class E_, class S_, bool VIRIAL, bool NT1_> struct DpdFamily
+template<class E_, class S_, bool VIRIAL, int NTM_> struct DpdFamily
     {
     typedef E_ E;
     typedef S_ S;
     typedef typename E::cache_type Cache;
-    static constexpr bool NT1 = NT1_;
+    static constexpr int NTM = NTM_;
 
-    PairTable<E, S> tab;
-    Cache c0;
-    S rc0;
+    TypeLookup<E, S, NTM> types;
     Vec4<S> vi;
     unsigned int tag_i;
     S fx = S(0), fy = S(0), fz = S(0), pe = S(0);
@@ -329,6 +417,7 @@ template<class E_, class S_, bool VIRIAL, bool NT1_> struct DpdFamily
 
     AZP_D void stage(const KernelArgs<S>& a, const typename E::param_type* params, unsigned int ntp)
         {
+        PairTable<E, S>& tab = types.tab;
         tab.carve(ntp);
         for (unsigned int t = threadIdx.x; t < ntp; t += blockDim.x)
             {
@@ -339,12 +428,12 @@ template<class E_, class S_, bool VIRIAL, bool NT1_> struct DpdFamily
         __syncthreads();
         tab.finish(ntp);
         __syncthreads();
-        c0 = tab.cache(0);
-        rc0 = tab.rcutsq(0);
+        types.after_stage();
         }
 
-    AZP_D void begin_row(const KernelArgs<S>& a, unsigned int i)
+    AZP_D void begin_row(const KernelArgs<S>& a, unsigned int i, unsigned int ti)
         {
+        types.begin_row(ti, a.ntypes);
         vi = load4(a.vel, i);
         tag_i = __ldg(a.tag + i);
         }
@@ -385,17 +474,12 @@ template<class E_, class S_, bool VIRIAL, bool NT1_> struct DpdFamily
         S dx, dy, dz;
         g.displacement(a.box, pj, dx, dy, dz);
         const S rsq = fma(dz, dz, fma(dy, dy, dx * dx));
-        if (NT1)
+        const unsigned int tj = NTM == 1 ? 0u : scalar_as_uint(pj.w);
+        const S rcutsq = types.rcutsq(tj);
+        if (rsq < rcutsq)
             {
-            if (rsq < rc0)
-                accept(a, c0, j, rsq, rc0, dx, dy, dz);
-            }
-        else
-            {
-            const unsigned int tp = index2d(a.ntypes, g.ti, scalar_as_uint(pj.w));
-            const S rcutsq = tab.rcutsq(tp);
-            if (rsq < rcutsq)
-                accept(a, tab.cache(tp), j, rsq, rcutsq, dx, dy, dz);
+            const Cache c = types.cache(tj);
+            accept(a, c, j, rsq, rcutsq, dx, dy, dz);
             }
         }
 
@@ -423,16 +507,14 @@ template<class E_, class S_, bool VIRIAL, bool NT1_> struct DpdFamily
 // Anisotropic family: gathers orientation_j; vector force, torque on i, energy,
 // virial 1/2 dx_a F_b.
 // =============================================================================================
-template<class E_, class S_, bool VIRIAL, bool NT1_> struct AnisoFamily
+template<class E_, class S_, bool VIRIAL, int NTM_> struct AnisoFamily
     {
     typedef E_ E;
     typedef S_ S;
     typedef typename E::cache_type Cache;
-    static constexpr bool NT1 = NT1_;
+    static constexpr int NTM = NTM_;
 
-    PairTable<E, S> tab;
-    Cache c0;
-    S rc0;
+    TypeLookup<E, S, NTM> types;
     Vec4<S> qi;
     S fx = S(0), fy = S(0), fz = S(0), pe = S(0);
     S tx = S(0), ty = S(0), tz = S(0);
@@ -445,6 +527,7 @@ template<class E_, class S_, bool VIRIAL, bool NT1_> struct AnisoFamily
 
     AZP_D void stage(const KernelArgs<S>& a, const typename E::param_type* params, unsigned int ntp)
         {
+        PairTable<E, S>& tab = types.tab;
         tab.carve(ntp);
         for (unsigned int t = threadIdx.x; t < ntp; t += blockDim.x)
             {
@@ -455,12 +538,12 @@ template<class E_, class S_, bool VIRIAL, bool NT1_> struct AnisoFamily
         __syncthreads();
         tab.finish(ntp);
         __syncthreads();
-        c0 = tab.cache(0);
-        rc0 = tab.rcutsq(0);
+        types.after_stage();
         }
 
-    AZP_D void begin_row(const KernelArgs<S>& a, unsigned int i)
+    AZP_D void begin_row(const KernelArgs<S>& a, unsigned int i, unsigned int ti)
         {
+        types.begin_row(ti, a.ntypes);
         qi = load4(a.orientation, i);
         }
 
@@ -498,17 +581,12 @@ template<class E_, class S_, bool VIRIAL, bool NT1_> struct AnisoFamily
         g.displacement(a.box, pj, dr.x, dr.y, dr.z);
         const S rsq = fma(dr.z, dr.z, fma(dr.y, dr.y, dr.x * dr.x));
         // the reference evaluator rejects only rsq > rcutsq (strictly), so accept rsq <= rcutsq
-        if (NT1)
+        const unsigned int tj = NTM == 1 ? 0u : scalar_as_uint(pj.w);
+        const S rcutsq = types.rcutsq(tj);
+        if (rsq <= rcutsq)
             {
-            if (rsq <= rc0)
-                accept(a, c0, j, rsq, rc0, dr);
-            }
-        else
-            {
-            const unsigned int tp = index2d(a.ntypes, g.ti, scalar_as_uint(pj.w));
-            const S rcutsq = tab.rcutsq(tp);
-            if (rsq <= rcutsq)
-                accept(a, tab.cache(tp), j, rsq, rcutsq, dr);
+            const Cache c = types.cache(tj);
+            accept(a, c, j, rsq, rcutsq, dr);
             }
         }
 
@@ -540,13 +618,13 @@ template<class E_, class S_, bool VIRIAL, bool NT1_> struct AnisoFamily
 // The kernel skeleton
 // =============================================================================================
 template<class Fam>
-__global__ void __launch_bounds__(kMaxBlock)
+__global__ void __launch_bounds__(max_block<typename Fam::S>())
     row_kernel(const __grid_constant__ KernelArgs<typename Fam::S> a,
                const typename Fam::E::param_type* __restrict__ params,
                const unsigned int tpp_log2)
     {
     typedef typename Fam::S S;
-    const unsigned int ntp = Fam::NT1 ? 1u : a.ntypes * a.ntypes;
+    const unsigned int ntp = Fam::NTM == 1 ? 1u : a.ntypes * a.ntypes;
     Fam fam;
     fam.stage(a, params, ntp);
 
@@ -575,49 +653,76 @@ __global__ void __launch_bounds__(kMaxBlock)
         {
         // the warp may skip the minimum-image wrap when the box is orthorhombic and fully
         // periodic and every active row of the warp is farther than rc_max from all faces
-        const S rc_max = fam.tab.rcutsq(ntp);
+        const S rc_max = fam.types.tab.rcutsq(ntp);
         const S m = S(0.49999);
         const bool inside = (fabs(g.pi.x) + rc_max < m * g.Lx) && (fabs(g.pi.y) + rc_max < m * g.Ly)
                             && (fabs(g.pi.z) + rc_max < m * g.Lz);
         g.skip_wrap = (a.box.flags == 2) && __all_sync(0xffffffffu, inside || !active);
         }
-    fam.begin_row(a, i);
+    fam.begin_row(a, i, g.ti);
 
     // ---- the row as aligned uint4 vectors of neighbour indices ------------------------------
-    // `pre` = entries between the 16-byte boundary below the row start and the row start.
+    // `pre` = entries between the 16-byte boundary below the row start and the row start; the
+    // valid entries of `base` are [pre, end). Full vectors are v in [v_begin, v_end); the (at
+    // most 3 + 3) entries in front of / behind them are handled by a guarded scalar epilogue, so
+    // rows may start at any head_list offset and nothing outside the row is ever read.
     const unsigned int* rowp = a.nlist + head;
     const unsigned int pre = (unsigned int)((reinterpret_cast<uintptr_t>(rowp) >> 2) & 3u);
     const unsigned int* base = rowp - pre;
-    const unsigned int end = pre + n; // valid entries of `base` are [pre, end)
+    const unsigned int end = pre + n;
     const uint4* base4 = reinterpret_cast<const uint4*>(base);
-    for (unsigned int v = lane; 4u * v < end; v += tpp)
+    const unsigned int v_begin = (pre + 3u) >> 2;
+    const unsigned int v_end = end >> 2;
+
+    // Software pipeline, two stages deep: the index vector is loaded two trips ahead (it streams
+    // from HBM: ~1 us), the four position gathers one trip ahead (L1/L2), so a lane always has
+    // one nlist load and four gathers in flight while it does the math of the current vector.
+    unsigned int v = v_begin + lane;
+    uint4 j_cur = make_uint4(0u, 0u, 0u, 0u), j_nxt = make_uint4(0u, 0u, 0u, 0u);
+    Vec4<S> p0, p1, p2, p3;
+    if (v < v_end)
         {
-        const unsigned int e = 4u * v;
-        if (e >= pre && e + 4u <= end)
+        j_cur = __ldg(base4 + v);
+        p0 = load4(a.pos, j_cur.x);
+        p1 = load4(a.pos, j_cur.y);
+        p2 = load4(a.pos, j_cur.z);
+        p3 = load4(a.pos, j_cur.w);
+        if (v + tpp < v_end)
+            j_nxt = __ldg(base4 + v + tpp);
+        }
+    while (v < v_end)
+        {
+        const unsigned int v1 = v + tpp, v2 = v1 + tpp;
+        const uint4 j = j_cur;
+        const Vec4<S> q0 = p0, q1 = p1, q2 = p2, q3 = p3;
+        if (v1 < v_end)
             {
-            const uint4 j = __ldg(base4 + v);
-            const Vec4<S> p0 = load4(a.pos, j.x);
-            const Vec4<S> p1 = load4(a.pos, j.y);
-            const Vec4<S> p2 = load4(a.pos, j.z);
-            const Vec4<S> p3 = load4(a.pos, j.w);
-            fam.pair(a, g, j.x, p0);
-            fam.pair(a, g, j.y, p1);
-            fam.pair(a, g, j.z, p2);
-            fam.pair(a, g, j.w, p3);
+            j_cur = j_nxt;
+            p0 = load4(a.pos, j_cur.x);
+            p1 = load4(a.pos, j_cur.y);
+            p2 = load4(a.pos, j_cur.z);
+            p3 = load4(a.pos, j_cur.w);
+            if (v2 < v_end)
+                j_nxt = __ldg(base4 + v2);
             }
-        else
+        fam.pair(a, g, j.x, q0);
+        fam.pair(a, g, j.y, q1);
+        fam.pair(a, g, j.z, q2);
+        fam.pair(a, g, j.w, q3);
+        v = v1;
+        }
+
+    // leftovers in front of and behind the full vectors
+        {
+        const unsigned int head_end = min(4u * v_begin, end);                   // [pre, head_end)
+        const unsigned int tail_begin = max(4u * v_end, head_end);              // [tail_begin, end)
+        const unsigned int n_left = (head_end - pre) + (end - tail_begin);      // <= 6
+        for (unsigned int q = lane; q < n_left; q += tpp)
             {
-            // partial vector at either end of the row: guarded scalar loads
-            for (unsigned int q = 0; q < 4u; ++q)
-                {
-                const unsigned int idx = e + q;
-                if (idx >= pre && idx < end)
-                    {
-                    const unsigned int j = __ldg(base + idx);
-                    const Vec4<S> pj = load4(a.pos, j);
-                    fam.pair(a, g, j, pj);
-                    }
-                }
+            const unsigned int idx = q < head_end - pre ? pre + q : tail_begin + (q - (head_end - pre));
+            const unsigned int j = __ldg(base + idx);
+            const Vec4<S> pj = load4(a.pos, j);
+            fam.pair(a, g, j, pj);
             }
         }
 

@@ -107,7 +107,8 @@ typedef struct azp_pair_args
     uint32_t ntypes;
     uint32_t shift_mode;     /* azp_shift_mode; DPD ignores it, aniso accepts none/shift */
     uint32_t compute_virial; /* 0/1 */
-    /* launch parameters (HOOMD's Autotuner<2> dimensions); 0 = let the library choose */
+    /* launch parameters (HOOMD's Autotuner<2> dimensions); 0 = let the library choose.
+     * block_size: multiple of 32, <= 512 (f32) / <= 256 (f64) */
     uint32_t block_size;
     uint32_t threads_per_particle; /* power of two <= 32 */
     /* DPD thermostat */
