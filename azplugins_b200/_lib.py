@@ -59,7 +59,7 @@ class AzpPairArgs(ctypes.Structure):
         ("block_size", ctypes.c_uint32),
         ("threads_per_particle", ctypes.c_uint32),
         ("seed", ctypes.c_uint32),
-        ("_pad0", ctypes.c_uint32),
+        ("n_max", ctypes.c_uint32),
         ("timestep", ctypes.c_uint64),
         ("deltaT", ctypes.c_double),
         ("T", ctypes.c_double),

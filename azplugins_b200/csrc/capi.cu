@@ -142,6 +142,32 @@ template<class S> static int unpack(int ev, const void* in, double* f)
     }
     } // namespace azp
 
+namespace azp
+    {
+cudaError_t long_row_scratch(cudaStream_t stream, LongRowScratch& out)
+    {
+    static std::mutex lock;
+    static std::map<std::pair<int, cudaStream_t>, LongRowScratch> table;
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess)
+        return err;
+    std::lock_guard<std::mutex> guard(lock);
+    LongRowScratch& s = table[std::make_pair(dev, stream)];
+    if (!s.queue)
+        {
+        unsigned int* mem = nullptr;
+        err = cudaMalloc(reinterpret_cast<void**>(&mem), sizeof(unsigned int) * (kLongRowCapacity + 4));
+        if (err != cudaSuccess)
+            return err;
+        s.count = mem;
+        s.queue = mem + 4;
+        }
+    out = s;
+    return cudaSuccess;
+    }
+    } // namespace azp
+
 using namespace azp;
 
 static int run_family(int family, int ev, int bits, const azp_pair_args* a, const void* p, cudaStream_t st)

@@ -87,6 +87,7 @@ template<class E, class S> class ContractEvaluator
         }
     // kernel-side entry points (see "kernel fast path" below): a contract-only evaluator keeps
     // its own cutoff / zero-parameter tests
+    static constexpr bool kWarpVote = true;
     AZP_HD static bool disabled(const cache_type&)
         {
         return false;

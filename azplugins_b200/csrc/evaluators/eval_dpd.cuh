@@ -75,6 +75,9 @@ template<class S> class DPDPairEvaluatorGeneralWeight : public PairEvaluatorBase
         m_dot = dot;
         }
 
+    // see IsoFamily::pair: skip the evaluator when no lane of the warp is inside the cutoff
+    static constexpr bool kWarpVote = false;
+
     AZP_HD static bool disabled(const cache_type&)
         {
         return false;

@@ -36,6 +36,9 @@ template<class S> class PairEvaluatorHertz : public PairEvaluatorBase<S>
         {
         }
 
+    // see IsoFamily::pair: skip the evaluator when no lane of the warp is inside the cutoff
+    static constexpr bool kWarpVote = true;
+
     AZP_HD static bool disabled(const cache_type& c)
         {
         return c.epsilon == S(0);

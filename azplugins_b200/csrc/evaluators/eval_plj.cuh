@@ -60,6 +60,9 @@ template<class S> class PairEvaluatorPerturbedLennardJones : public PairEvaluato
         {
         }
 
+    // see IsoFamily::pair: skip the evaluator when no lane of the warp is inside the cutoff
+    static constexpr bool kWarpVote = false;
+
     AZP_HD static bool disabled(const cache_type& c)
         {
         return c.lj1 == S(0);

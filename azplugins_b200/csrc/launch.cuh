@@ -9,8 +9,23 @@
 #include "../../include/azp_b200.h"
 #include "pair_kernels.cuh"
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 namespace azp
     {
+// ---- long-row deferral scratch: one small queue per (device, stream), allocated on first use --
+constexpr unsigned int kLongRowThreshold = 512; // rows longer than this go to the second pass
+constexpr unsigned int kLongRowCapacity = 1u << 16;
+struct LongRowScratch
+    {
+    unsigned int* queue = nullptr;
+    unsigned int* count = nullptr;
+    };
+// defined once in capi.cu
+cudaError_t long_row_scratch(cudaStream_t stream, LongRowScratch& out);
+
 template<class S> inline BoxDim<S> convert_box(const azp_box& b)
     {
     BoxDim<S> o;
@@ -56,6 +71,10 @@ template<class S> inline KernelArgs<S> convert_args(const azp_pair_args& a)
     k.timestep = (unsigned int)(a.timestep & 0xffffffffull);
     k.deltaT = S(a.deltaT);
     k.T = S(a.T);
+    k.long_queue = nullptr;
+    k.long_count = nullptr;
+    k.long_capacity = 0;
+    k.long_threshold = kLongRowThreshold;
     return k;
     }
 
@@ -135,18 +154,52 @@ template<class K> inline cudaError_t ensure_smem(K kernel, size_t bytes)
     return cudaSuccess;
     }
 
-template<class E, class S, bool XPLOR, bool VIRIAL, int NTM>
-inline cudaError_t launch_pair_variant(const KernelArgs<S>& k, const void* d_params, const LaunchShape& s, cudaStream_t stream)
+// Launch the main pass and, when the caller announced long rows (n_max) and the rows are split
+// over fewer than 32 lanes, the warp-per-row second pass over the deferred rows.
+template<class Fam>
+inline cudaError_t launch_rows(KernelArgs<typename Fam::S> k, const void* d_params, const LaunchShape& s, unsigned int n_max, cudaStream_t stream)
     {
-    typedef IsoFamily<E, S, XPLOR, VIRIAL, NTM> Fam;
-    const size_t ntp = NTM == 1 ? 1 : size_t(k.ntypes) * k.ntypes;
-    const size_t smem = Fam::smem_bytes(ntp);
-    auto kernel = row_kernel<Fam>;
-    cudaError_t err = ensure_smem(kernel, smem);
+    typedef typename Fam::E E;
+    const size_t ntp = Fam::NTM == 1 ? 1 : size_t(k.ntypes) * k.ntypes;
+    const typename E::param_type* params = static_cast<const typename E::param_type*>(d_params);
+    const bool defer = n_max > kLongRowThreshold && s.tpp_log2 < 5;
+    cudaError_t err;
+    if (defer)
+        {
+        LongRowScratch scratch;
+        err = long_row_scratch(stream, scratch);
+        if (err != cudaSuccess)
+            return err;
+        err = cudaMemsetAsync(scratch.count, 0, sizeof(unsigned int), stream);
+        if (err != cudaSuccess)
+            return err;
+        k.long_queue = scratch.queue;
+        k.long_count = scratch.count;
+        k.long_capacity = kLongRowCapacity;
+        }
+    auto kernel = row_kernel<Fam, false>;
+    const size_t smem = Fam::smem_bytes(ntp, s.block);
+    err = ensure_smem(kernel, smem);
     if (err != cudaSuccess)
         return err;
-    kernel<<<s.grid, s.block, smem, stream>>>(k, static_cast<const typename E::param_type*>(d_params), s.tpp_log2);
+    kernel<<<s.grid, s.block, smem, stream>>>(k, params, s.tpp_log2);
+    err = cudaGetLastError();
+    if (err != cudaSuccess || !defer)
+        return err;
+    auto long_kernel = row_kernel<Fam, true>;
+    const unsigned int long_block = 128;
+    const size_t long_smem = Fam::smem_bytes(ntp, long_block);
+    err = ensure_smem(long_kernel, long_smem);
+    if (err != cudaSuccess)
+        return err;
+    long_kernel<<<148 * 4, long_block, long_smem, stream>>>(k, params, 5u);
     return cudaGetLastError();
+    }
+
+template<class E, class S, bool XPLOR, bool VIRIAL, int NTM>
+inline cudaError_t launch_pair_variant(const KernelArgs<S>& k, const void* d_params, const LaunchShape& s, unsigned int n_max, cudaStream_t stream)
+    {
+    return launch_rows<IsoFamily<E, S, XPLOR, VIRIAL, NTM>>(k, d_params, s, n_max, stream);
     }
 
 template<class E, class S> cudaError_t launch_pair(const azp_pair_args* a, const void* d_params, cudaStream_t stream)
@@ -167,7 +220,7 @@ template<class E, class S> cudaError_t launch_pair(const azp_pair_args* a, const
     const int ntm = a->ntypes == 1 ? 1 : (a->ntypes == 2 ? 2 : 0);
 #define AZP_CASE(X, V, T)           \
     if (xplor == X && vir == V && ntm == T) \
-        return launch_pair_variant<E, S, X, V, T>(k, d_params, s, stream);
+        return launch_pair_variant<E, S, X, V, T>(k, d_params, s, a->n_max, stream);
     AZP_CASE(false, false, 0)
     AZP_CASE(false, false, 1)
     AZP_CASE(false, false, 2)
@@ -185,17 +238,9 @@ template<class E, class S> cudaError_t launch_pair(const azp_pair_args* a, const
     }
 
 template<class E, class S, bool VIRIAL, int NTM>
-inline cudaError_t launch_dpd_variant(const KernelArgs<S>& k, const void* d_params, const LaunchShape& s, cudaStream_t stream)
+inline cudaError_t launch_dpd_variant(const KernelArgs<S>& k, const void* d_params, const LaunchShape& s, unsigned int n_max, cudaStream_t stream)
     {
-    typedef DpdFamily<E, S, VIRIAL, NTM> Fam;
-    const size_t ntp = NTM == 1 ? 1 : size_t(k.ntypes) * k.ntypes;
-    const size_t smem = Fam::smem_bytes(ntp);
-    auto kernel = row_kernel<Fam>;
-    cudaError_t err = ensure_smem(kernel, smem);
-    if (err != cudaSuccess)
-        return err;
-    kernel<<<s.grid, s.block, smem, stream>>>(k, static_cast<const typename E::param_type*>(d_params), s.tpp_log2);
-    return cudaGetLastError();
+    return launch_rows<DpdFamily<E, S, VIRIAL, NTM>>(k, d_params, s, n_max, stream);
     }
 
 template<class E, class S> cudaError_t launch_dpd(const azp_pair_args* a, const void* d_params, cudaStream_t stream)
@@ -217,30 +262,22 @@ template<class E, class S> cudaError_t launch_dpd(const azp_pair_args* a, const 
     if (vir)
         {
         if (ntm == 1)
-            return launch_dpd_variant<E, S, true, 1>(k, d_params, s, stream);
+            return launch_dpd_variant<E, S, true, 1>(k, d_params, s, a->n_max, stream);
         if (ntm == 2)
-            return launch_dpd_variant<E, S, true, 2>(k, d_params, s, stream);
-        return launch_dpd_variant<E, S, true, 0>(k, d_params, s, stream);
+            return launch_dpd_variant<E, S, true, 2>(k, d_params, s, a->n_max, stream);
+        return launch_dpd_variant<E, S, true, 0>(k, d_params, s, a->n_max, stream);
         }
     if (ntm == 1)
-        return launch_dpd_variant<E, S, false, 1>(k, d_params, s, stream);
+        return launch_dpd_variant<E, S, false, 1>(k, d_params, s, a->n_max, stream);
     if (ntm == 2)
-        return launch_dpd_variant<E, S, false, 2>(k, d_params, s, stream);
-    return launch_dpd_variant<E, S, false, 0>(k, d_params, s, stream);
+        return launch_dpd_variant<E, S, false, 2>(k, d_params, s, a->n_max, stream);
+    return launch_dpd_variant<E, S, false, 0>(k, d_params, s, a->n_max, stream);
     }
 
 template<class E, class S, bool VIRIAL, int NTM>
-inline cudaError_t launch_aniso_variant(const KernelArgs<S>& k, const void* d_params, const LaunchShape& s, cudaStream_t stream)
+inline cudaError_t launch_aniso_variant(const KernelArgs<S>& k, const void* d_params, const LaunchShape& s, unsigned int n_max, cudaStream_t stream)
     {
-    typedef AnisoFamily<E, S, VIRIAL, NTM> Fam;
-    const size_t ntp = NTM == 1 ? 1 : size_t(k.ntypes) * k.ntypes;
-    const size_t smem = Fam::smem_bytes(ntp);
-    auto kernel = row_kernel<Fam>;
-    cudaError_t err = ensure_smem(kernel, smem);
-    if (err != cudaSuccess)
-        return err;
-    kernel<<<s.grid, s.block, smem, stream>>>(k, static_cast<const typename E::param_type*>(d_params), s.tpp_log2);
-    return cudaGetLastError();
+    return launch_rows<AnisoFamily<E, S, VIRIAL, NTM>>(k, d_params, s, n_max, stream);
     }
 
 template<class E, class S> cudaError_t launch_aniso(const azp_pair_args* a, const void* d_params, cudaStream_t stream)
@@ -264,16 +301,16 @@ template<class E, class S> cudaError_t launch_aniso(const azp_pair_args* a, cons
     if (vir)
         {
         if (ntm == 1)
-            return launch_aniso_variant<E, S, true, 1>(k, d_params, s, stream);
+            return launch_aniso_variant<E, S, true, 1>(k, d_params, s, a->n_max, stream);
         if (ntm == 2)
-            return launch_aniso_variant<E, S, true, 2>(k, d_params, s, stream);
-        return launch_aniso_variant<E, S, true, 0>(k, d_params, s, stream);
+            return launch_aniso_variant<E, S, true, 2>(k, d_params, s, a->n_max, stream);
+        return launch_aniso_variant<E, S, true, 0>(k, d_params, s, a->n_max, stream);
         }
     if (ntm == 1)
-        return launch_aniso_variant<E, S, false, 1>(k, d_params, s, stream);
+        return launch_aniso_variant<E, S, false, 1>(k, d_params, s, a->n_max, stream);
     if (ntm == 2)
-        return launch_aniso_variant<E, S, false, 2>(k, d_params, s, stream);
-    return launch_aniso_variant<E, S, false, 0>(k, d_params, s, stream);
+        return launch_aniso_variant<E, S, false, 2>(k, d_params, s, a->n_max, stream);
+    return launch_aniso_variant<E, S, false, 0>(k, d_params, s, a->n_max, stream);
     }
     } // namespace azp
 

@@ -62,6 +62,12 @@ template<class S> struct KernelArgs
     unsigned int timestep;
     S deltaT;
     S T;
+    // long-row deferral (see row_kernel): rows longer than long_threshold are queued by the main
+    // pass and evaluated by a second pass with a whole warp per row
+    unsigned int* long_queue;
+    unsigned int* long_count;
+    unsigned int long_capacity;
+    unsigned int long_threshold;
     };
 
 // largest block_size accepted: 512 threads (<= 128 registers) for fp32; the fp64 variants hold
@@ -235,6 +241,19 @@ template<class E, class S, int NTM> struct TypeLookup
             rcB = tab.rcutsq(index2d(2u, t, 1u));
             }
         }
+    // true when the potential is switched off for every partner type of this row's particle
+    // (all effective cutoffs are zero): the row then contributes nothing and is not streamed
+    AZP_D bool row_disabled() const
+        {
+        if (NTM == 1)
+            return !(rcA > S(0));
+        if (NTM == 2)
+            return !(rcA > S(0)) && !(rcB > S(0));
+        bool off = true;
+        for (unsigned int tj = 0; tj < ntypes; ++tj)
+            off = off && !(tab.rcutsq(index2d(ntypes, ti, tj)) > S(0));
+        return off;
+        }
     AZP_D unsigned int pair_index(unsigned int tj) const
         {
         return NTM == 1 ? 0u : index2d(NTM == 2 ? 2u : ntypes, ti, tj);
@@ -266,13 +285,14 @@ template<class E_, class S_, bool XPLOR, bool VIRIAL, int NTM_> struct IsoFamily
     typedef S_ S;
     typedef typename E::cache_type Cache;
     static constexpr int NTM = NTM_;
+    static constexpr int PIPE = 2;
 
     TypeLookup<E, S, NTM> types;
     unsigned int xplor_off;
     S fx = S(0), fy = S(0), fz = S(0), pe = S(0);
     Virial6<S> w;
 
-    AZP_HD static size_t smem_bytes(size_t ntp)
+    AZP_HD static size_t smem_bytes(size_t ntp, size_t)
         {
         return PairTable<E, S>::bytes(ntp) + (XPLOR ? ntp * sizeof(XplorEntry<S>) : 0) + 32;
         }
@@ -346,10 +366,17 @@ template<class E_, class S_, bool XPLOR, bool VIRIAL, int NTM_> struct IsoFamily
             }
         else
             {
-            // Branch-free: in a 32-lane warp some neighbour is always inside the cutoff, so a
-            // branch around the evaluator is never skipped and only costs BSSY/BRA/BSYNC. Every
-            // lane evaluates; rejected lanes are zeroed by a select (which also discards any
-            // inf/NaN the evaluator produced for an out-of-range rsq).
+            // Warp-level test instead of a per-lane branch. In a dense fluid some lane of the
+            // warp is always inside the cutoff, so a divergent branch around the evaluator is
+            // never skipped and only costs BSSY/BRA/BSYNC: when any lane needs the evaluator,
+            // every lane runs it and rejected lanes are zeroed by a select (which also discards
+            // any inf/NaN produced for an out-of-range rsq). When NO lane is inside -- potentials
+            // that are switched off for most type pairs, e.g. Hertz acting only between colloids
+            // -- the whole warp skips the evaluation and the accumulation with one uniform branch.
+            // Evaluators opt in with kWarpVote (the vote costs two issue slots per neighbour,
+            // which the cheap dense-fluid potentials, PLJ and Yukawa, do not get back).
+            if (E::kWarpVote && __ballot_sync(__activemask(), inside) == 0u)
+                return;
             const Cache c = types.cache(tj);
             S f = S(0), e = S(0);
             E eval(rsq, rcutsq, c);
@@ -371,6 +398,12 @@ template<class E_, class S_, bool XPLOR, bool VIRIAL, int NTM_> struct IsoFamily
             w.yz = fma(dy, vz, w.yz);
             w.zz = fma(dz, vz, w.zz);
             }
+        }
+
+    AZP_D void reset()
+        {
+        fx = fy = fz = pe = S(0);
+        w = Virial6<S>();
         }
 
     AZP_D void finish(const KernelArgs<S>& a, unsigned int row, bool writer, unsigned int tpp)
@@ -403,6 +436,7 @@ template<class E_, class S_, bool VIRIAL, int NTM_> struct DpdFamily
     typedef S_ S;
     typedef typename E::cache_type Cache;
     static constexpr int NTM = NTM_;
+    static constexpr int PIPE = 0;
 
     TypeLookup<E, S, NTM> types;
     Vec4<S> vi;
@@ -410,7 +444,7 @@ template<class E_, class S_, bool VIRIAL, int NTM_> struct DpdFamily
     S fx = S(0), fy = S(0), fz = S(0), pe = S(0);
     Virial6<S> w;
 
-    AZP_HD static size_t smem_bytes(size_t ntp)
+    AZP_HD static size_t smem_bytes(size_t ntp, size_t)
         {
         return PairTable<E, S>::bytes(ntp) + 16;
         }
@@ -483,6 +517,12 @@ template<class E_, class S_, bool VIRIAL, int NTM_> struct DpdFamily
             }
         }
 
+    AZP_D void reset()
+        {
+        fx = fy = fz = pe = S(0);
+        w = Virial6<S>();
+        }
+
     AZP_D void finish(const KernelArgs<S>& a, unsigned int row, bool writer, unsigned int tpp)
         {
         for (unsigned int o = tpp >> 1; o > 0; o >>= 1)
@@ -513,6 +553,7 @@ template<class E_, class S_, bool VIRIAL, int NTM_> struct AnisoFamily
     typedef S_ S;
     typedef typename E::cache_type Cache;
     static constexpr int NTM = NTM_;
+    static constexpr int PIPE = 0;
 
     TypeLookup<E, S, NTM> types;
     Vec4<S> qi;
@@ -520,7 +561,7 @@ template<class E_, class S_, bool VIRIAL, int NTM_> struct AnisoFamily
     S tx = S(0), ty = S(0), tz = S(0);
     Virial6<S> w;
 
-    AZP_HD static size_t smem_bytes(size_t ntp)
+    AZP_HD static size_t smem_bytes(size_t ntp, size_t)
         {
         return PairTable<E, S>::bytes(ntp) + 16;
         }
@@ -590,6 +631,13 @@ template<class E_, class S_, bool VIRIAL, int NTM_> struct AnisoFamily
             }
         }
 
+    AZP_D void reset()
+        {
+        fx = fy = fz = pe = S(0);
+        tx = ty = tz = S(0);
+        w = Virial6<S>();
+        }
+
     AZP_D void finish(const KernelArgs<S>& a, unsigned int row, bool writer, unsigned int tpp)
         {
         for (unsigned int o = tpp >> 1; o > 0; o >>= 1)
@@ -617,32 +665,19 @@ template<class E_, class S_, bool VIRIAL, int NTM_> struct AnisoFamily
 // =============================================================================================
 // The kernel skeleton
 // =============================================================================================
+// One row for one group of `tpp` lanes: geometry, neighbour stream, reduction, store.
 template<class Fam>
-__global__ void __launch_bounds__(max_block<typename Fam::S>())
-    row_kernel(const __grid_constant__ KernelArgs<typename Fam::S> a,
-               const typename Fam::E::param_type* __restrict__ params,
-               const unsigned int tpp_log2)
+AZP_D void process_row(Fam& fam,
+                       const KernelArgs<typename Fam::S>& a,
+                       const unsigned int ntp,
+                       const unsigned int row,
+                       unsigned int n,
+                       const uint64_t head,
+                       const bool active,
+                       const unsigned int lane,
+                       const unsigned int tpp)
     {
     typedef typename Fam::S S;
-    const unsigned int ntp = Fam::NTM == 1 ? 1u : a.ntypes * a.ntypes;
-    Fam fam;
-    fam.stage(a, params, ntp);
-
-    // ---- which row, which lane of the row's group ----------------------------------------
-    const unsigned int tpp = 1u << tpp_log2;
-    const unsigned int gtid = blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned int slot = gtid >> tpp_log2;
-    const unsigned int lane = gtid & (tpp - 1u);
-    const unsigned int nslots = a.row_ids ? a.n_row_ids : a.N;
-    const bool active = slot < nslots;
-    unsigned int row = 0, n = 0;
-    uint64_t head = 0;
-    if (active)
-        {
-        row = a.row_ids ? __ldg(a.row_ids + slot) : slot;
-        n = __ldg(a.n_neigh + row);
-        head = __ldg(a.head_list + row);
-        }
     const unsigned int i = active ? row + a.row_offset : 0u;
 
     RowGeometry<S> g;
@@ -660,6 +695,8 @@ __global__ void __launch_bounds__(max_block<typename Fam::S>())
         g.skip_wrap = (a.box.flags == 2) && __all_sync(0xffffffffu, inside || !active);
         }
     fam.begin_row(a, i, g.ti);
+    if (fam.types.row_disabled())
+        n = 0; // e.g. Hertz acting only between colloids: solvent rows just write zeros
 
     // ---- the row as aligned uint4 vectors of neighbour indices ------------------------------
     // `pre` = entries between the 16-byte boundary below the row start and the row start; the
@@ -674,42 +711,63 @@ __global__ void __launch_bounds__(max_block<typename Fam::S>())
     const unsigned int v_begin = (pre + 3u) >> 2;
     const unsigned int v_end = end >> 2;
 
-    // Software pipeline, two stages deep: the index vector is loaded two trips ahead (it streams
-    // from HBM: ~1 us), the four position gathers one trip ahead (L1/L2), so a lane always has
-    // one nlist load and four gathers in flight while it does the math of the current vector.
+    // Software pipeline. PIPE = 2: the index vector is loaded two trips ahead (it streams from
+    // HBM: ~1 us) and the four position gathers one trip ahead (L1/L2), so a lane always has one
+    // nlist load and four gathers in flight while it does the math of the current vector --
+    // best for the cheap isotropic evaluators. PIPE = 0: load, gather, compute in program order
+    // with the smallest register footprint -- best for the heavy DPD / anisotropic evaluators,
+    // which hide latency with occupancy instead (measured).
     unsigned int v = v_begin + lane;
-    uint4 j_cur = make_uint4(0u, 0u, 0u, 0u), j_nxt = make_uint4(0u, 0u, 0u, 0u);
-    Vec4<S> p0, p1, p2, p3;
-    if (v < v_end)
+    if (Fam::PIPE == 2)
         {
-        j_cur = __ldg(base4 + v);
-        p0 = load4(a.pos, j_cur.x);
-        p1 = load4(a.pos, j_cur.y);
-        p2 = load4(a.pos, j_cur.z);
-        p3 = load4(a.pos, j_cur.w);
-        if (v + tpp < v_end)
-            j_nxt = __ldg(base4 + v + tpp);
-        }
-    while (v < v_end)
-        {
-        const unsigned int v1 = v + tpp, v2 = v1 + tpp;
-        const uint4 j = j_cur;
-        const Vec4<S> q0 = p0, q1 = p1, q2 = p2, q3 = p3;
-        if (v1 < v_end)
+        uint4 j_cur = make_uint4(0u, 0u, 0u, 0u), j_nxt = make_uint4(0u, 0u, 0u, 0u);
+        Vec4<S> p0, p1, p2, p3;
+        if (v < v_end)
             {
-            j_cur = j_nxt;
+            j_cur = __ldg(base4 + v);
             p0 = load4(a.pos, j_cur.x);
             p1 = load4(a.pos, j_cur.y);
             p2 = load4(a.pos, j_cur.z);
             p3 = load4(a.pos, j_cur.w);
-            if (v2 < v_end)
-                j_nxt = __ldg(base4 + v2);
+            if (v + tpp < v_end)
+                j_nxt = __ldg(base4 + v + tpp);
             }
-        fam.pair(a, g, j.x, q0);
-        fam.pair(a, g, j.y, q1);
-        fam.pair(a, g, j.z, q2);
-        fam.pair(a, g, j.w, q3);
-        v = v1;
+        while (v < v_end)
+            {
+            const unsigned int v1 = v + tpp, v2 = v1 + tpp;
+            const uint4 j = j_cur;
+            const Vec4<S> q0 = p0, q1 = p1, q2 = p2, q3 = p3;
+            if (v1 < v_end)
+                {
+                j_cur = j_nxt;
+                p0 = load4(a.pos, j_cur.x);
+                p1 = load4(a.pos, j_cur.y);
+                p2 = load4(a.pos, j_cur.z);
+                p3 = load4(a.pos, j_cur.w);
+                if (v2 < v_end)
+                    j_nxt = __ldg(base4 + v2);
+                }
+            fam.pair(a, g, j.x, q0);
+            fam.pair(a, g, j.y, q1);
+            fam.pair(a, g, j.z, q2);
+            fam.pair(a, g, j.w, q3);
+            v = v1;
+            }
+        }
+    else
+        {
+        for (; v < v_end; v += tpp)
+            {
+            const uint4 j = __ldg(base4 + v);
+            const Vec4<S> q0 = load4(a.pos, j.x);
+            const Vec4<S> q1 = load4(a.pos, j.y);
+            const Vec4<S> q2 = load4(a.pos, j.z);
+            const Vec4<S> q3 = load4(a.pos, j.w);
+            fam.pair(a, g, j.x, q0);
+            fam.pair(a, g, j.y, q1);
+            fam.pair(a, g, j.z, q2);
+            fam.pair(a, g, j.w, q3);
+            }
         }
 
     // leftovers in front of and behind the full vectors
@@ -727,6 +785,83 @@ __global__ void __launch_bounds__(max_block<typename Fam::S>())
         }
 
     fam.finish(a, row, active && lane == 0, tpp);
+    }
+
+// LONGPASS = false: the main pass, one row per group of tpp lanes. When the caller announced
+// rows longer than long_threshold (azp_pair_args.n_max) and tpp < 32, such rows are not
+// evaluated here: lane 0 of the group queues the row and the group moves on, so one 1,800-entry
+// colloid row no longer holds a 2-lane group (and its CTA slot) for the duration of ~15 ordinary
+// rows. LONGPASS = true: the second pass, launched with tpp = 32 on a fixed grid; every warp
+// takes queued rows until the queue is empty. If the queue overflows, the main pass evaluates
+// the row in place, so correctness never depends on the queue capacity.
+template<class Fam, bool LONGPASS>
+__global__ void __launch_bounds__(max_block<typename Fam::S>())
+    row_kernel(const __grid_constant__ KernelArgs<typename Fam::S> a,
+               const typename Fam::E::param_type* __restrict__ params,
+               const unsigned int tpp_log2)
+    {
+    const unsigned int ntp = Fam::NTM == 1 ? 1u : a.ntypes * a.ntypes;
+    Fam fam;
+    fam.stage(a, params, ntp);
+
+    const unsigned int tpp = 1u << tpp_log2;
+    const unsigned int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned int lane = gtid & (tpp - 1u);
+    if (!LONGPASS)
+        {
+        const unsigned int slot = gtid >> tpp_log2;
+        const unsigned int nslots = a.row_ids ? a.n_row_ids : a.N;
+        bool active = slot < nslots;
+        unsigned int row = 0, n = 0;
+        uint64_t head = 0;
+        if (active)
+            {
+            row = a.row_ids ? __ldg(a.row_ids + slot) : slot;
+            n = __ldg(a.n_neigh + row);
+            head = __ldg(a.head_list + row);
+            if (a.long_queue && n > a.long_threshold)
+                {
+                // every lane of the group takes the same decision: lane 0 reserves the slot and
+                // broadcasts the outcome through the group's shuffle
+                unsigned int pos = 0xffffffffu;
+                if (lane == 0)
+                    {
+                    pos = atomicAdd(a.long_count, 1u);
+                    if (pos < a.long_capacity)
+                        a.long_queue[pos] = row;
+                    }
+                pos = __shfl_sync(__activemask(), pos, 0, tpp);
+                if (pos < a.long_capacity)
+                    {
+                    active = false; // deferred: the second pass writes this row
+                    n = 0;
+                    }
+                }
+            }
+        process_row(fam, a, ntp, row, n, head, active, lane, tpp);
+        }
+    else
+        {
+        const unsigned int nslots = min(*a.long_count, a.long_capacity);
+        const unsigned int groups = (gridDim.x * blockDim.x) >> tpp_log2;
+        const unsigned int per_warp = 32u >> tpp_log2;
+        // warp-uniform trip count: the groups of a warp walk the queue together
+        for (unsigned int s0 = ((gtid >> 5) * per_warp); s0 < nslots; s0 += groups)
+            {
+            const unsigned int slot = s0 + ((gtid & 31u) >> tpp_log2);
+            const bool active = slot < nslots;
+            unsigned int row = 0, n = 0;
+            uint64_t head = 0;
+            if (active)
+                {
+                row = a.long_queue[slot];
+                n = __ldg(a.n_neigh + row);
+                head = __ldg(a.head_list + row);
+                }
+            fam.reset();
+            process_row(fam, a, ntp, row, n, head, active, lane, tpp);
+            }
+        }
     }
     } // namespace azp
 

@@ -22,7 +22,7 @@ def fill_args(*, box, pos, n_neigh, nlist, head_list, rcutsq, ntypes, force, n_r
               ronsq=None, virial=None, torque=None, vel=None, orientation=None, tag=None,
               shift_mode=0, compute_virial=False, block_size=0, threads_per_particle=0,
               seed=0, timestep=0, dt=0.0, kT=0.0, row_offset=0, row_ids=None,
-              size_neigh_list=None):
+              size_neigh_list=None, n_max=0):
     a = _lib.AzpPairArgs()
     a.d_force = _ptr(force)
     a.d_virial = _ptr(virial)
@@ -46,6 +46,7 @@ def fill_args(*, box, pos, n_neigh, nlist, head_list, rcutsq, ntypes, force, n_r
     a.block_size = int(block_size)
     a.threads_per_particle = int(threads_per_particle)
     a.seed = int(seed) & 0xFFFF
+    a.n_max = int(n_max)
     a.timestep = int(timestep)
     a.deltaT = float(dt)
     a.T = float(kT)

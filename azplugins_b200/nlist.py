@@ -32,6 +32,7 @@ class NeighborList:
         self.nlist = None
         self.head_list = None
         self.size = 0
+        self.n_max = 0  # largest row capacity (HOOMD's n_max)
         self.num_builds = 0
         self._pos_at_build = None
         self._external = False
@@ -65,6 +66,7 @@ class NeighborList:
         self.nlist = conv(nlist, np.uint32, np.int32)
         self.head_list = conv(head_list, np.uint64, np.int64)
         self.size = int(self.nlist.numel())
+        self.n_max = int(self.n_neigh.max().item()) if self.n_neigh.numel() else 0
         self._external = True
         return self
 
@@ -165,6 +167,7 @@ class Cell(NeighborList):
                     cap[sel] = m
             head = torch.cumsum(cap, 0) - cap
             size = int(cap.sum())
+            self.n_max = int(cap.max().item()) if n_rows else 0
             nlist = torch.zeros(max(size, 1), dtype=torch.int32, device=dev)
             a.d_head_list = head.data_ptr()
             a.d_nlist = nlist.data_ptr()

@@ -214,6 +214,7 @@ class Pair:
             n_rows=st.N, shift_mode=_lib.SHIFT_MODES[self._mode], compute_virial=compute_virial,
             block_size=self._launch_shape[0], threads_per_particle=self._launch_shape[1],
             timestep=ts, size_neigh_list=self.nlist.size, row_ids=row_ids,
+            n_max=self.nlist.n_max,
             **self._extra_args(ts))
 
     def compute(self, timestep=None, compute_virial=True, row_ids=None):

@@ -113,7 +113,10 @@ typedef struct azp_pair_args
     uint32_t threads_per_particle; /* power of two <= 32 */
     /* DPD thermostat */
     uint32_t seed;     /* uint16 range */
-    uint32_t _pad0;
+    /* largest row capacity of the list (HOOMD pair_args_t::n_max); 0 = unknown. When it exceeds
+     * 512 the library defers rows longer than that to a second warp-per-row pass (row-length
+     * skew, e.g. colloids in solvent). Results do not depend on it. */
+    uint32_t n_max;
     uint64_t timestep; /* truncated to 32 bits like the reference evaluator does */
     double deltaT;
     double T;

@@ -205,6 +205,7 @@ template<class Args> inline azp_pair_args common_args(const Args& a)
     o.d_rcutsq = a.d_rcutsq;
     o.box = flatten_box(a.box);
     o.N = a.N;
+    o.n_max = a.n_max;
     o.ntypes = a.ntypes;
     o.shift_mode = a.shift_mode;
     o.compute_virial = a.compute_virial;
