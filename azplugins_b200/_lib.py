@@ -106,6 +106,7 @@ EXPORTED_SYMBOLS = (
     "azp_aniso_forces_f32",
     "azp_aniso_forces_f64",
     "azp_autotune",
+    "azp_gather_rows",
     "azp_dpd_alpha",
     "azp_philox4x32_10",
     "azp_nlist_cell_dim",
@@ -151,6 +152,8 @@ def _load():
     lib.azp_autotune.argtypes = [i32, i32, i32, ctypes.POINTER(AzpPairArgs), vp, vp,
                                  ctypes.POINTER(u32), ctypes.POINTER(u32),
                                  ctypes.POINTER(ctypes.c_float)]
+    lib.azp_gather_rows.argtypes = [vp, vp, ctypes.c_uint64, u32, vp, vp]
+    lib.azp_gather_rows.restype = i32
     lib.azp_dpd_alpha.argtypes = [i32, u32, u32, u32, ctypes.c_uint64]
     lib.azp_dpd_alpha.restype = ctypes.c_double
     lib.azp_philox4x32_10.argtypes = [vp, vp, vp]

@@ -237,8 +237,37 @@ template<class S, bool FILL> static int rows(const azp_nlist_args* a, cudaStream
     }
     } // namespace azp
 
+namespace azp
+    {
+// d_dst[k] = d_src[d_idx[k]], rows of `chunks` 16-byte pieces; thread t moves piece t % chunks of
+// row t / chunks, so the stores are fully coalesced and the loads are 16-byte gathers.
+__global__ void gather_rows_kernel(const uint4* __restrict__ src, const long long* __restrict__ idx, unsigned long long n, unsigned int chunks, uint4* __restrict__ dst)
+    {
+    const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * chunks)
+        return;
+    const unsigned long long k = t / chunks;
+    const unsigned int c = (unsigned int)(t - k * chunks);
+    dst[t] = __ldg(src + (unsigned long long)idx[k] * chunks + c);
+    }
+    } // namespace azp
+
 extern "C"
     {
+    int azp_gather_rows(const void* d_src, const int64_t* d_idx, uint64_t n, uint32_t row_bytes, void* d_dst, void* stream)
+        {
+        if (n == 0)
+            return 0;
+        if (!d_src || !d_idx || !d_dst || row_bytes == 0 || row_bytes % 16 != 0)
+            return (int)cudaErrorInvalidValue;
+        const unsigned int chunks = row_bytes / 16;
+        const unsigned long long threads = n * chunks;
+        const unsigned int block = 256;
+        azp::gather_rows_kernel<<<(unsigned int)((threads + block - 1) / block), block, 0, (cudaStream_t)stream>>>(
+            static_cast<const uint4*>(d_src), reinterpret_cast<const long long*>(d_idx), n, chunks, static_cast<uint4*>(d_dst));
+        return (int)cudaGetLastError();
+        }
+
     // Largest grid with cells no smaller than r_list_max. An axis that cannot hold three such
     // cells gets a single cell (the stencil then covers it once and minimum image does the rest).
     int azp_nlist_cell_dim(const azp_box* box, double r_list_max, uint32_t dim[3])

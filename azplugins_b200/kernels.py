@@ -117,3 +117,14 @@ def philox4x32_10(ctr, key):
     out = np.zeros(4, dtype=np.uint32)
     _lib.lib.azp_philox4x32_10(c.ctypes.data, k.ctypes.data, out.ctypes.data)
     return out
+
+
+def gather_rows(src, idx, out, stream=None):
+    """out[k] = src[idx[k]] for 2-D Scalar4 tensors on the GPU (halo packing)."""
+    if stream is None:
+        stream = torch.cuda.current_stream().cuda_stream
+    row_bytes = src.shape[1] * src.element_size()
+    rc = _lib.lib.azp_gather_rows(src.data_ptr(), idx.data_ptr(), int(idx.numel()), row_bytes,
+                                  out.data_ptr(), ctypes.c_void_p(stream))
+    _lib.check(rc, "gather_rows")
+    return out

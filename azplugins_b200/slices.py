@@ -141,20 +141,40 @@ class HaloExchange:
                     ops.append(dist.P2POp(dist.irecv, a[o:o + c], r, group=self.group))
         return ops, packs
 
-    def __call__(self, arrays):
-        """Update the ghost region of every array in ``arrays`` from the owners (in place)."""
-        if not self.peers:
-            return
+    def _ops_for(self, arrays):
         key = tuple(a.data_ptr() for a in arrays)
         if key not in self._buf:
             self._buf.clear()
             self._buf[key] = self._plan_ops(arrays)
-        ops, packs = self._buf[key]
+        return self._buf[key]
+
+    def pack(self, arrays):
+        """Gather the particles the peers asked for into the persistent send buffers (a few
+        microseconds: one coalesced kernel of the library on CUDA, index_select on the CPU)."""
+        if not self.peers:
+            return
+        _, packs = self._ops_for(arrays)
         n_local = self.plan.n_local
         for a, sbuf in packs:
-            torch.index_select(a[:n_local], 0, self._send_cat, out=sbuf)  # pack
+            if a.is_cuda:
+                from . import kernels
+
+                kernels.gather_rows(a, self._send_cat, sbuf)
+            else:
+                torch.index_select(a[:n_local], 0, self._send_cat, out=sbuf)
+
+    def exchange(self, arrays):
+        """Post the sends/receives of the packed buffers straight into the ghost regions."""
+        if not self.peers:
+            return
+        ops, _ = self._ops_for(arrays)
         for req in dist.batch_isend_irecv(ops):
             req.wait()
+
+    def __call__(self, arrays):
+        """Update the ghost region of every array in ``arrays`` from the owners (in place)."""
+        self.pack(arrays)
+        self.exchange(arrays)
 
 
 class SliceScheduler:
@@ -168,8 +188,11 @@ class SliceScheduler:
         self.exchange_arrays = exchange_arrays
         self.halo = HaloExchange(plan, group)
         self.n_local = plan.n_local
-        self.comm_stream = torch.cuda.Stream(device=state.device)
+        # high priority: the few CTAs of the pack / NCCL send-recv kernels must be scheduled
+        # between the thousands of CTAs of the interior-row kernel, not after them
+        self.comm_stream = torch.cuda.Stream(device=state.device, priority=-1)
         self._halo_done = torch.cuda.Event()
+        self._packed = torch.cuda.Event()
         self._step_done = torch.cuda.Event()
         self._step_done.record()
         self.launches_per_step = len(pots) * ((1 if plan.interior_rows.numel() else 0)
@@ -228,12 +251,19 @@ class SliceScheduler:
         cur = torch.cuda.current_stream()
         # the exchange may overwrite ghosts only after the previous step's boundary rows are done
         self.comm_stream.wait_event(self._step_done)
-        # interior rows first: they are already running while the host posts the exchange
+        # pack on the compute stream (microseconds), then the interior rows, and only the NCCL
+        # send/recv on the communication stream: measured on B200, NCCL's two CTAs slip in between
+        # the CTAs of the interior kernel, while a bandwidth kernel on a second stream does not
+        # (the interior kernel holds every register file), so the pack must not sit there
+        cur.wait_event(self._step_done)
+        self.halo.pack(self.exchange_arrays)
+        self._packed.record()
         if p.interior_rows.numel():
             for pot in self.pots:
                 pot.compute(compute_virial=compute_virial, row_ids=p.interior_rows)
+        self.comm_stream.wait_event(self._packed)
         with torch.cuda.stream(self.comm_stream):
-            self.halo(self.exchange_arrays)
+            self.halo.exchange(self.exchange_arrays)
             self._halo_done.record()
         cur.wait_event(self._halo_done)
         if p.boundary_rows.numel():

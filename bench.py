@@ -31,6 +31,18 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 METRIC = "pair_force_particle_steps_per_s"
 UNIT = "particle-steps/s"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the
@@ -206,7 +218,7 @@ def run_reference(args):
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # -------------------------------------------------------------------------------------------------
@@ -226,7 +238,11 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if multi:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL's internal stream must outrank the force kernels, or its few CTAs queue behind the
+        # thousands of CTAs of the interior-row kernel and the exchange serialises with the compute
+        opts = dist.ProcessGroupNCCL.Options()
+        opts.is_high_priority_stream = True
+        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
     n_per = args.n_per_gpu or DEFAULT_N[args.workload]
     wl = synth.CONFIGS[args.workload](N=n_per * world)
     n_total = wl.N
@@ -394,12 +410,18 @@ def run_b200(args):
     elif rank == 0:
         line["cpu_baseline"] = None
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if multi:
         dist.destroy_process_group()
 
 
 def main():
+    # the contract is ONE JSON line on stdout: libraries (NCCL prints its version banner there)
+    # are kept off it by pointing fd 1 at stderr until the line is written
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args = parse()
     if args.impl == "reference":
         run_reference(args)

@@ -163,6 +163,11 @@ int azp_autotune(int family, int evaluator, int scalar_bits, const azp_pair_args
                  const void* d_params, void* stream, uint32_t* best_block, uint32_t* best_tpp,
                  float* best_ms);
 
+/* Halo packing for the multi-GPU particle-slice scheduler: d_dst[k] = d_src[d_idx[k]] for rows of
+ * row_bytes (a multiple of 16: Scalar4 = 16 or 32). One coalesced 16-byte store per thread. */
+int azp_gather_rows(const void* d_src, const int64_t* d_idx, uint64_t n, uint32_t row_bytes,
+                    void* d_dst, void* stream);
+
 /* Uniform(-1,1) value the DPD evaluator draws for a pair (host side; same code as the kernel).
  * Exposes the RNG keying of src/DPDPairEvaluatorGeneralWeight.h:213-233 for parity tests. */
 double azp_dpd_alpha(int scalar_bits, uint32_t seed, uint32_t tag_i, uint32_t tag_j, uint64_t timestep);
