@@ -13,7 +13,7 @@ import os
 import torch  # noqa: F401
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libazp_b200.so")
+LIB_PATH = os.environ.get("AZP_B200_LIB", os.path.join(HERE, "libazp_b200.so"))  # override: A/B builds
 
 EV_PERTURBED_LENNARD_JONES = 0
 EV_EXPANDED_YUKAWA = 1
