@@ -91,8 +91,7 @@ inline bool is_pow2(unsigned int x)
     }
 
 // Launch parameters: honour the caller's (block_size, threads_per_particle) -- HOOMD's autotuner
-// dimensions -- or choose from the mean row capacity: about 12-16 neighbours per lane keeps the
-// tail waste of a row under 5 % while leaving enough rows per warp for coalesced outputs.
+// dimensions -- or choose them from the mean row capacity and the number of rows.
 inline cudaError_t choose_shape(const azp_pair_args& a, LaunchShape& s, unsigned int block_limit)
     {
     unsigned int block = a.block_size ? a.block_size : 128u;
@@ -103,10 +102,15 @@ inline cudaError_t choose_shape(const azp_pair_args& a, LaunchShape& s, unsigned
         {
         const unsigned int rows = a.N ? a.N : 1u;
         const double mean_cap = a.size_neigh_list ? double(a.size_neigh_list) / rows : 64.0;
-        // rows are consumed four entries per lane per trip: ~48+ entries per lane keeps the
-        // fixed per-thread prologue and the shuffle reduction under 10 % of the row
+        // Measured on B200: the kernels are instruction-issue bound, so the fewest
+        // lanes per row win (least reduction / prologue work per neighbour) as long as the grid
+        // fills the machine: one lane per row up to ~160 neighbours, then split long rows, then
+        // split further until there are about five CTAs per SM.
         tpp = 1;
-        while (tpp < 32u && mean_cap / tpp > 80.0)
+        while (tpp < 32u && mean_cap / tpp > 160.0)
+            tpp <<= 1;
+        const unsigned long long nslots = a.d_row_ids ? a.n_row_ids : a.N;
+        while (tpp < 32u && nslots * tpp / block < 148ull * 5ull)
             tpp <<= 1;
         }
     if (!is_pow2(tpp) || tpp > 32u)

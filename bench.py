@@ -47,7 +47,11 @@ METRIC = "pair_force_particle_steps_per_s"
 UNIT = "particle-steps/s"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the
 # committed `ncu --set full` capture of this command (profiles/); None until captured.
-NCU_TRAFFIC_BYTES = {"C2": None}
+NCU_TRAFFIC_BYTES = {"C2": 614.26e6}  # profiles/r01_c2_ncu_full_v5_summary.csv (577.12 + 37.14 MB)
+# warp instructions executed per launch of the same capture (smsp__inst_executed.sum): the kernel
+# is instruction-issue bound, not HBM bound, so the issue floor is reported beside the HBM roofline
+NCU_WARP_INSTRUCTIONS = {"C2": 226.94e6}
+SM_COUNT, SCHEDULERS_PER_SM = 148, 4
 
 
 def parse():
@@ -385,6 +389,12 @@ def run_b200(args):
                 "kernel_ms": kern_ms, "algorithmic_bytes_per_step": alg_bytes,
                 "bytes_per_particle": (bytes_fixed + 4.0 * n_bar) * n_pot,
                 "mean_row_length": n_bar, "launches_per_step": launches_per_step}
+    if args.workload in NCU_WARP_INSTRUCTIONS and not multi and clocks.get("sm_mhz"):
+        # informational co-limiter: one warp instruction per scheduler per clock
+        floor_ms = (NCU_WARP_INSTRUCTIONS[args.workload] * (n_local / 1.0e6)
+                    / (SM_COUNT * SCHEDULERS_PER_SM * clocks["sm_mhz"] * 1e6) * 1e3)
+        roofline["issue_floor_ms"] = floor_ms
+        roofline["issue_frac"] = floor_ms / kern_ms
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
