@@ -107,6 +107,7 @@ EXPORTED_SYMBOLS = (
     "azp_aniso_forces_f64",
     "azp_autotune",
     "azp_gather_rows",
+    "azp_push_rows",
     "azp_dpd_alpha",
     "azp_philox4x32_10",
     "azp_nlist_cell_dim",
@@ -154,6 +155,8 @@ def _load():
                                  ctypes.POINTER(ctypes.c_float)]
     lib.azp_gather_rows.argtypes = [vp, vp, ctypes.c_uint64, u32, vp, vp]
     lib.azp_gather_rows.restype = i32
+    lib.azp_push_rows.argtypes = [vp, vp, vp, ctypes.c_uint64, u32, vp]
+    lib.azp_push_rows.restype = i32
     lib.azp_dpd_alpha.argtypes = [i32, u32, u32, u32, ctypes.c_uint64]
     lib.azp_dpd_alpha.restype = ctypes.c_double
     lib.azp_philox4x32_10.argtypes = [vp, vp, vp]

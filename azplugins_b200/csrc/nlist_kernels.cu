@@ -252,8 +252,40 @@ __global__ void gather_rows_kernel(const uint4* __restrict__ src, const long lon
     }
     } // namespace azp
 
+namespace azp
+    {
+// *(row at dst_addr[k]) = src[idx[k]]: the halo PUSH. The destination addresses may be peer-mapped
+// (another GPU's ghost region reached over NVLink); consecutive k of one peer are consecutive
+// addresses, so the 16-byte stores coalesce into full NVLink write packets.
+__global__ void push_rows_kernel(const uint4* __restrict__ src, const long long* __restrict__ idx, const unsigned long long* __restrict__ dst_addr, unsigned long long n, unsigned int chunks)
+    {
+    const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * chunks)
+        return;
+    const unsigned long long k = t / chunks;
+    const unsigned int c = (unsigned int)(t - k * chunks);
+    uint4* dst = reinterpret_cast<uint4*>(dst_addr[k]) + c;
+    *dst = __ldg(src + (unsigned long long)idx[k] * chunks + c);
+    }
+    } // namespace azp
+
 extern "C"
     {
+    int azp_push_rows(const void* d_src, const int64_t* d_idx, const uint64_t* d_dst_addr, uint64_t n, uint32_t row_bytes, void* stream)
+        {
+        if (n == 0)
+            return 0;
+        if (!d_src || !d_idx || !d_dst_addr || row_bytes == 0 || row_bytes % 16 != 0)
+            return (int)cudaErrorInvalidValue;
+        const unsigned int chunks = row_bytes / 16;
+        const unsigned long long threads = n * chunks;
+        const unsigned int block = 256;
+        azp::push_rows_kernel<<<(unsigned int)((threads + block - 1) / block), block, 0, (cudaStream_t)stream>>>(
+            static_cast<const uint4*>(d_src), reinterpret_cast<const long long*>(d_idx),
+            reinterpret_cast<const unsigned long long*>(d_dst_addr), n, chunks);
+        return (int)cudaGetLastError();
+        }
+
     int azp_gather_rows(const void* d_src, const int64_t* d_idx, uint64_t n, uint32_t row_bytes, void* d_dst, void* stream)
         {
         if (n == 0)

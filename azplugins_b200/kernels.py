@@ -128,3 +128,14 @@ def gather_rows(src, idx, out, stream=None):
                                   out.data_ptr(), ctypes.c_void_p(stream))
     _lib.check(rc, "gather_rows")
     return out
+
+
+def push_rows(src, idx, dst_addr, stream=None):
+    """*(row at dst_addr[k]) = src[idx[k]] -- halo push; ``dst_addr`` (int64 tensor of device
+    addresses) may point into peer GPUs' memory (symmetric-memory buffers over NVLink)."""
+    if stream is None:
+        stream = torch.cuda.current_stream().cuda_stream
+    row_bytes = src.shape[1] * src.element_size()
+    rc = _lib.lib.azp_push_rows(src.data_ptr(), idx.data_ptr(), dst_addr.data_ptr(),
+                                int(idx.numel()), row_bytes, ctypes.c_void_p(stream))
+    _lib.check(rc, "push_rows")

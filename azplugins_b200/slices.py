@@ -95,6 +95,11 @@ class SlicePlan:
             return self
         gathered = [None] * self.world
         dist.all_gather_object(gathered, wanted, group=group)
+        # first ghost row (local index) of every owner's segment on every rank: the destination
+        # of a peer-memory push (PeerHalo)
+        starts = [None] * self.world
+        dist.all_gather_object(starts, [int(self.n_local + o) for o in self.recv_offsets], group=group)
+        self.peer_ghost_start = np.asarray(starts, dtype=np.int64)  # [receiver][owner]
         dev = self.ghost_ids.device
         self.send_idx = []
         for r in range(self.world):
@@ -177,16 +182,89 @@ class HaloExchange:
         self.exchange(arrays)
 
 
+class PeerHalo:
+    """Halo exchange over NVLink peer memory instead of NCCL send/recv.
+
+    The exchanged arrays live in symmetric memory (``torch.distributed._symmetric_memory``: the
+    same allocation on every rank, peer-mapped). One kernel of the library (``azp_push_rows``)
+    stores the particles a peer needs straight into that peer's ghost region -- consecutive
+    16-byte stores per peer, fire-and-forget over NVLink -- bracketed by two device-side
+    barriers on the symmetric-memory signal pads:
+
+        barrier   every rank has finished reading its ghosts (its previous force kernel precedes
+                  the barrier in stream order), so they may be overwritten
+        push      my particles -> the peers' ghost regions
+        barrier   every push has landed; the force kernel may read the ghosts
+
+    No pack buffer, no second stream, no interior/boundary split: the rows run in one launch in
+    natural order right after the second barrier.
+    """
+
+    def __init__(self, plan, arrays, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.plan = plan
+        self.group = group if group is not None else dist.group.WORLD
+        world, me = plan.world, plan.rank
+        self.peers = [r for r in range(world) if r != me and plan.send_counts[r] > 0]
+        dev = arrays[0].device
+        n_rows = torch.tensor([arrays[0].shape[0]], dtype=torch.int64, device=dev)
+        dist.all_reduce(n_rows, op=dist.ReduceOp.MAX, group=self.group)
+        max_rows = int(n_rows.item())
+        self.arrays, self.handles, self.dst_addr = [], [], []
+        self._send_cat = torch.cat([plan.send_idx[r] for r in self.peers]) if self.peers else None
+        for a in arrays:
+            sym = symm_mem.empty((max_rows, a.shape[1]), dtype=a.dtype, device=dev)
+            sym[:a.shape[0]].copy_(a)
+            hdl = symm_mem.rendezvous(sym, self.group)
+            row_bytes = a.shape[1] * a.element_size()
+            addr = []
+            for r in self.peers:
+                start = int(plan.peer_ghost_start[r][me])
+                base = int(hdl.buffer_ptrs[r]) + start * row_bytes
+                addr.append(base + row_bytes * torch.arange(int(plan.send_counts[r]), dtype=torch.int64))
+            self.arrays.append(sym[:a.shape[0]])
+            self.handles.append(hdl)
+            self.dst_addr.append(torch.cat(addr).to(dev) if addr else None)
+
+    def bytes_per_step(self):
+        n = int(sum(self.plan.recv_counts[r] for r in range(self.plan.world) if r != self.plan.rank))
+        return sum(n * a.shape[1] * a.element_size() for a in self.arrays)
+
+    def __call__(self):
+        """Enqueue barrier, push, barrier on the current stream."""
+        from . import kernels
+
+        h = self.handles[0]
+        h.barrier(channel=0)
+        if self.peers:
+            for a, dst in zip(self.arrays, self.dst_addr):
+                kernels.push_rows(a, self._send_cat, dst)
+        h.barrier(channel=1)
+
+
 class SliceScheduler:
     """One rank's slice of a workload: local+ghost State, remapped list, potentials, exchange."""
 
-    def __init__(self, plan, state, nlist, pots, exchange_arrays, group=None):
+    def __init__(self, plan, state, nlist, pots, exchange_arrays, group=None, transport="nccl"):
         self.plan = plan
         self.state = state
         self.nlist = nlist
         self.pots = pots
         self.exchange_arrays = exchange_arrays
+        self.transport = transport
         self.halo = HaloExchange(plan, group)
+        self.peer_halo = None
+        if transport == "peer":
+            # move the exchanged arrays into symmetric memory; the State keeps views of them
+            self.peer_halo = PeerHalo(plan, exchange_arrays, group)
+            for name in ("pos", "vel", "orientation"):
+                for old, new in zip(exchange_arrays, self.peer_halo.arrays):
+                    if getattr(state, name) is old:
+                        setattr(state, name, new)
+            self.exchange_arrays = list(self.peer_halo.arrays)
+        elif transport != "nccl":
+            raise ValueError("transport must be 'nccl' or 'peer'")
         self.n_local = plan.n_local
         # high priority: the few CTAs of the pack / NCCL send-recv kernels must be scheduled
         # between the thousands of CTAs of the interior-row kernel, not after them
@@ -195,13 +273,17 @@ class SliceScheduler:
         self._packed = torch.cuda.Event()
         self._step_done = torch.cuda.Event()
         self._step_done.record()
-        self.launches_per_step = len(pots) * ((1 if plan.interior_rows.numel() else 0)
-                                              + (1 if plan.boundary_rows.numel() else 0))
+        if transport == "peer":
+            self.launches_per_step = len(pots) + len(self.exchange_arrays)
+        else:
+            self.launches_per_step = len(pots) * ((1 if plan.interior_rows.numel() else 0)
+                                                  + (1 if plan.boundary_rows.numel() else 0))
         self._host = None
 
     # ---- construction from a synthetic workload ------------------------------------------
     @classmethod
-    def from_workload(cls, wl, rank, world, device, dtype=np.float32, buffer=0.4, group=None):
+    def from_workload(cls, wl, rank, world, device, dtype=np.float32, buffer=0.4, group=None,
+                      transport="nccl"):
         """Every rank generates the same global workload (seeded), builds the rows of its slice
         on its GPU, derives the plan and keeps only local + ghost particles."""
         from . import nlist as aznlist
@@ -237,10 +319,12 @@ class SliceScheduler:
             arrays.append(state.vel)
         if "TwoPatchMorse" in names:
             arrays.append(state.orientation)
-        return cls(plan, state, local_list, pots, arrays, group)
+        return cls(plan, state, local_list, pots, arrays, group, transport)
 
     # ---- per step ------------------------------------------------------------------------
     def exchange_bytes_per_step(self):
+        if self.peer_halo is not None:
+            return self.peer_halo.bytes_per_step()
         return self.halo.bytes_per_step(self.exchange_arrays)
 
     def mean_row_length(self):
@@ -248,6 +332,12 @@ class SliceScheduler:
 
     def step(self, compute_virial=False):
         p = self.plan
+        if self.peer_halo is not None:
+            # barrier, push over NVLink, barrier, then every row in one launch per potential
+            self.peer_halo()
+            for pot in self.pots:
+                pot.compute(compute_virial=compute_virial)
+            return
         cur = torch.cuda.current_stream()
         # the exchange may overwrite ghosts only after the previous step's boundary rows are done
         self.comm_stream.wait_event(self._step_done)
@@ -274,12 +364,17 @@ class SliceScheduler:
     def tune(self, compute_virial=False):
         """Autotune each potential's launch shape on the interior rows."""
         out = []
-        self.halo(self.exchange_arrays)
+        if self.peer_halo is not None:
+            self.peer_halo()
+        else:
+            self.halo(self.exchange_arrays)
         torch.cuda.synchronize()
         for pot in self.pots:
             pot.nlist.check_dist = False
-            args = pot._args(None, compute_virial, self.plan.interior_rows
-                             if self.plan.interior_rows.numel() else None)
+            rows = None
+            if self.peer_halo is None and self.plan.interior_rows.numel():
+                rows = self.plan.interior_rows
+            args = pot._args(None, compute_virial, rows)
             from . import kernels
 
             b, t, ms = kernels.autotune(pot._family, pot._evaluator, pot._bits, args,
@@ -294,6 +389,10 @@ class SliceScheduler:
         torch.cuda.synchronize()
         e0.record()
         for _ in range(steps):
+            if self.peer_halo is not None:
+                for pot in self.pots:
+                    pot.compute(compute_virial=compute_virial)
+                continue
             for rows in (self.plan.interior_rows, self.plan.boundary_rows):
                 if rows.numel():
                     for pot in self.pots:

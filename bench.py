@@ -62,6 +62,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3", "C4", "C5"])
     ap.add_argument("--n-per-gpu", type=int, default=0, help="override particles per GPU")
+    ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
+                    help="multi-GPU halo transport: NVLink peer-memory push (default) or NCCL send/recv")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-tune", action="store_true")
     ap.add_argument("--block", type=int, default=0, help="pin block_size (with --no-tune)")
@@ -285,7 +287,7 @@ def run_b200(args):
         from azplugins_b200 import slices
 
         sched = slices.SliceScheduler.from_workload(wl, rank, world, dev, dtype=np.float32,
-                                                    buffer=synth.BUFFER)
+                                                    buffer=synth.BUFFER, transport=args.transport)
         if not args.no_tune:
             tuned = sched.tune(compute_virial=wl.compute_virial)
         else:
@@ -407,8 +409,9 @@ def run_b200(args):
                                     "from HBM every step; positions stay L2-resident by design"
                                     % (4e-6 * n_bar * n_local),
                        "parallelism": "1 GPU" if not multi else
-                       "%d particle slices, NCCL halo exchange (%.1f MB/step/rank)"
-                       % (world, exchange_bytes / 1e6)},
+                       "%d particle slices, %s (%.1f MB/step/rank)"
+                       % (world, "halo pushed over NVLink peer memory" if args.transport == "peer"
+                          else "NCCL halo exchange", exchange_bytes / 1e6)},
             "roofline": roofline, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": max(e2e_ms, e2e_wall_ms) / K},

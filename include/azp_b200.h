@@ -168,6 +168,12 @@ int azp_autotune(int family, int evaluator, int scalar_bits, const azp_pair_args
 int azp_gather_rows(const void* d_src, const int64_t* d_idx, uint64_t n, uint32_t row_bytes,
                     void* d_dst, void* stream);
 
+/* Halo push over peer memory: row k of the send list goes to the address d_dst_addr[k], which may
+ * be a peer-mapped address of another GPU's ghost region (NVLink P2P stores; the caller orders the
+ * push against the readers with barriers). row_bytes as above. */
+int azp_push_rows(const void* d_src, const int64_t* d_idx, const uint64_t* d_dst_addr, uint64_t n,
+                  uint32_t row_bytes, void* stream);
+
 /* Uniform(-1,1) value the DPD evaluator draws for a pair (host side; same code as the kernel).
  * Exposes the RNG keying of src/DPDPairEvaluatorGeneralWeight.h:213-233 for parity tests. */
 double azp_dpd_alpha(int scalar_bits, uint32_t seed, uint32_t tag_i, uint32_t tag_j, uint64_t timestep);
