@@ -22,12 +22,12 @@ def fill_args(*, box, pos, n_neigh, nlist, head_list, rcutsq, ntypes, force, n_r
               ronsq=None, virial=None, torque=None, vel=None, orientation=None, tag=None,
               shift_mode=0, compute_virial=False, block_size=0, threads_per_particle=0,
               seed=0, timestep=0, dt=0.0, kT=0.0, row_offset=0, row_ids=None,
-              size_neigh_list=None, n_max=0):
+              size_neigh_list=None, n_max=0, virial_pitch=None):
     a = _lib.AzpPairArgs()
     a.d_force = _ptr(force)
     a.d_virial = _ptr(virial)
     a.d_torque = _ptr(torque)
-    a.virial_pitch = 0 if virial is None else int(virial.shape[-1])
+    a.virial_pitch = 0 if virial is None else int(virial.shape[-1] if virial_pitch is None else virial_pitch)
     a.d_pos = _ptr(pos)
     a.d_vel = _ptr(vel)
     a.d_orientation = _ptr(orientation)

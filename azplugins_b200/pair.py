@@ -199,7 +199,7 @@ class Pair:
     def _extra_args(self, timestep):
         return {}
 
-    def _args(self, timestep=None, compute_virial=True, row_ids=None):
+    def _args(self, timestep=None, compute_virial=True, row_ids=None, rows=None):
         st = self._state
         if st is None:
             raise RuntimeError("potential is not attached to a State")
@@ -207,24 +207,78 @@ class Pair:
         if self.nlist.storage_mode != "full":
             raise RuntimeError("GPU pair potentials need a full neighbour list")
         ts = st.timestep if timestep is None else int(timestep)
+        lo, hi = (0, st.N) if rows is None else (int(rows[0]), int(rows[1]))
+        if not (0 <= lo <= hi <= st.N):
+            raise ValueError("rows must satisfy 0 <= lo <= hi <= N")
+        extra = self._extra_args(ts)
+        if "torque" in extra:
+            extra["torque"] = extra["torque"][lo:hi]
+        # a contiguous row range is the same launch on offset views of the per-row arrays
+        # (n_neigh, head_list, outputs); per-particle inputs stay whole and are indexed with
+        # row_offset, the virial keeps its full pitch
         return kernels.fill_args(
-            box=st.box, pos=st.pos, n_neigh=self.nlist.n_neigh, nlist=self.nlist.nlist,
-            head_list=self.nlist.head_list, rcutsq=self._d_rcutsq, ronsq=self._d_ronsq,
-            ntypes=st.ntypes, force=self._force, virial=self._virial if compute_virial else None,
-            n_rows=st.N, shift_mode=_lib.SHIFT_MODES[self._mode], compute_virial=compute_virial,
+            box=st.box, pos=st.pos, n_neigh=self.nlist.n_neigh[lo:hi], nlist=self.nlist.nlist,
+            head_list=self.nlist.head_list[lo:hi], rcutsq=self._d_rcutsq, ronsq=self._d_ronsq,
+            ntypes=st.ntypes, force=self._force[lo:hi],
+            virial=self._virial[:, lo:hi] if compute_virial else None,
+            virial_pitch=self._virial.shape[1],
+            n_rows=hi - lo, row_offset=lo, shift_mode=_lib.SHIFT_MODES[self._mode],
+            compute_virial=compute_virial,
             block_size=self._launch_shape[0], threads_per_particle=self._launch_shape[1],
             timestep=ts, size_neigh_list=self.nlist.size, row_ids=row_ids,
             n_max=self.nlist.n_max,
-            **self._extra_args(ts))
+            **extra)
 
-    def compute(self, timestep=None, compute_virial=True, row_ids=None):
+    def compute(self, timestep=None, compute_virial=True, row_ids=None, rows=None):
         """``ForceCompute::compute(timestep)``: enqueue the kernel on the current stream.
         ``row_ids`` (int32 device tensor) restricts the evaluation to those rows (scheduler use:
-        interior rows while the halo exchange is in flight, boundary rows after)."""
-        args = self._args(timestep, compute_virial, row_ids)
+        interior rows while the halo exchange is in flight, boundary rows after); ``rows`` =
+        ``(lo, hi)`` to a contiguous range (used by :meth:`compute_to_host`)."""
+        if row_ids is not None and rows is not None:
+            raise ValueError("give row_ids or rows, not both")
+        args = self._args(timestep, compute_virial, row_ids, rows)
+        if args.N == 0:
+            return self
         with torch.cuda.device(self._state.device):
             kernels.launch(self._family, self._evaluator, self._bits, args, self._d_params.data_ptr())
         self._computed = True
+        return self
+
+    def compute_to_host(self, host_force, host_virial=None, host_torque=None, timestep=None,
+                        chunks=4):
+        """Evaluate and deliver the per-particle results into pinned host tensors, overlapping the
+        device-to-host copies with the computation: the rows are evaluated in ``chunks``
+        contiguous ranges and every finished range is copied on a second stream while the next
+        one runs (the copy of 40 MB of forces + virials takes 2.5x the C2 kernel, so the step is
+        bounded by PCIe, not by kernel + copy). Synchronises before returning."""
+        st = self._state
+        if st is None:
+            raise RuntimeError("potential is not attached to a State")
+        compute_virial = host_virial is not None
+        cur = torch.cuda.current_stream(st.device)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=st.device)
+            self._chunk_events = []
+        while len(self._chunk_events) < chunks:
+            self._chunk_events.append(torch.cuda.Event())
+        n = st.N
+        bounds = [(n * c) // chunks for c in range(chunks + 1)]
+        for c in range(chunks):
+            lo, hi = bounds[c], bounds[c + 1]
+            if hi == lo:
+                continue
+            self.compute(timestep=timestep, compute_virial=compute_virial, rows=(lo, hi))
+            ev = self._chunk_events[c]
+            ev.record(cur)
+            with torch.cuda.stream(self._copy_stream):
+                self._copy_stream.wait_event(ev)
+                host_force[lo:hi].copy_(self._force[lo:hi], non_blocking=True)
+                if compute_virial:
+                    for k in range(6):  # six contiguous segments of the (6, N) array
+                        host_virial[k, lo:hi].copy_(self._virial[k, lo:hi], non_blocking=True)
+                if host_torque is not None:
+                    host_torque[lo:hi].copy_(self._torque[lo:hi], non_blocking=True)
+        self._copy_stream.synchronize()
         return self
 
     def tune_kernel_parameters(self, timestep=None, compute_virial=True):

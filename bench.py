@@ -339,13 +339,11 @@ def run_b200(args):
             d2h += host_virial.numel() * host_virial.element_size() * len(pots)
 
         def e2e_step():
+            # the call a user makes: positions from pinned host memory in, per-particle forces
+            # (+ virials) delivered to pinned host memory (row chunks, copies overlapped)
             state.pos.copy_(host_pos, non_blocking=True)
             for p in pots:
-                p.compute(compute_virial=wl.compute_virial)
-                host_force.copy_(p._force, non_blocking=True)
-                if wl.compute_virial:
-                    host_virial.copy_(p._virial, non_blocking=True)
-            torch.cuda.current_stream().synchronize()  # the caller reads the result every step
+                p.compute_to_host(host_force, host_virial if wl.compute_virial else None)
     else:
         h2d, d2h = sched.e2e_bytes(wl.compute_virial)
         e2e_step = lambda: sched.e2e_step(compute_virial=wl.compute_virial)  # noqa: E731
