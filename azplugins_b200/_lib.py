@@ -35,6 +35,25 @@ class AzpBox(ctypes.Structure):
     ]
 
 
+class AzpBarrierArgs(ctypes.Structure):
+    _fields_ = [
+        ("d_force", ctypes.c_void_p),
+        ("d_virial", ctypes.c_void_p),
+        ("virial_pitch", ctypes.c_uint64),
+        ("d_pos", ctypes.c_void_p),
+        ("d_params", ctypes.c_void_p),
+        ("box", AzpBox),
+        ("location", ctypes.c_double),
+        ("N", ctypes.c_uint32),
+        ("ntypes", ctypes.c_uint32),
+        ("geometry", ctypes.c_int32),
+        ("block_size", ctypes.c_uint32),
+    ]
+
+
+BARRIER_PLANAR, BARRIER_SPHERICAL = 0, 1
+
+
 class AzpPairArgs(ctypes.Structure):
     _fields_ = [
         ("d_force", ctypes.c_void_p),
@@ -108,6 +127,9 @@ EXPORTED_SYMBOLS = (
     "azp_autotune",
     "azp_gather_rows",
     "azp_push_rows",
+    "azp_harmonic_barrier_f32",
+    "azp_harmonic_barrier_f64",
+    "azp_harmonic_barrier_valid",
     "azp_dpd_alpha",
     "azp_philox4x32_10",
     "azp_nlist_cell_dim",
@@ -157,6 +179,12 @@ def _load():
     lib.azp_gather_rows.restype = i32
     lib.azp_push_rows.argtypes = [vp, vp, vp, ctypes.c_uint64, u32, vp]
     lib.azp_push_rows.restype = i32
+    for sfx in ("_f32", "_f64"):
+        fn = getattr(lib, "azp_harmonic_barrier" + sfx)
+        fn.argtypes = [ctypes.POINTER(AzpBarrierArgs), vp]
+        fn.restype = i32
+    lib.azp_harmonic_barrier_valid.argtypes = [i32, i32, ctypes.c_double, ctypes.POINTER(AzpBox)]
+    lib.azp_harmonic_barrier_valid.restype = i32
     lib.azp_dpd_alpha.argtypes = [i32, u32, u32, u32, ctypes.c_uint64]
     lib.azp_dpd_alpha.restype = ctypes.c_double
     lib.azp_philox4x32_10.argtypes = [vp, vp, vp]

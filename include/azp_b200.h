@@ -174,6 +174,39 @@ int azp_gather_rows(const void* d_src, const int64_t* d_idx, uint64_t n, uint32_
 int azp_push_rows(const void* d_src, const int64_t* d_idx, const uint64_t* d_dst_addr, uint64_t n,
                   uint32_t row_bytes, void* stream);
 
+/* External harmonic barriers. Replaces
+ *   gpu::compute_harmonic_barrier<BarrierEvaluatorT>(d_force, d_virial, d_pos, d_params,
+ *       global_box, evaluator, N, ntypes, block_size)        reference src/HarmonicBarrierGPU.cuh:100-132
+ * for BarrierEvaluatorT = PlanarBarrierEvaluator (src/PlanarBarrierEvaluator.h:31-63: plane normal
+ * to +y at y = location) and SphericalBarrierEvaluator (src/SphericalBarrierEvaluator.h:30-67:
+ * sphere of radius location about the origin). d_params is the reference's Scalar2[ntypes]
+ * {k, offset} (src/HarmonicBarrier.h:120-122); positions are wrapped into the box first (:86-88);
+ * the virial array is zeroed in the same pass (:129). Bit-identical to the reference CPU class. */
+enum azp_barrier_geometry
+    {
+    AZP_BARRIER_PLANAR = 0,
+    AZP_BARRIER_SPHERICAL = 1
+    };
+typedef struct azp_barrier_args
+    {
+    void* d_force;        /* Scalar4[N], overwritten */
+    void* d_virial;       /* Scalar[6 * virial_pitch], zeroed; may be NULL */
+    uint64_t virial_pitch;
+    const void* d_pos;    /* Scalar4[N] */
+    const void* d_params; /* Scalar2[ntypes] {k, offset} */
+    azp_box box;          /* global box */
+    double location;      /* the Variant's value at this timestep: H (planar) or R (spherical) */
+    uint32_t N;
+    uint32_t ntypes;
+    int32_t geometry;     /* azp_barrier_geometry */
+    uint32_t block_size;  /* 0 = library default (256); multiple of 32, <= 256 */
+    } azp_barrier_args;
+int azp_harmonic_barrier_f32(const azp_barrier_args* args, void* stream);
+int azp_harmonic_barrier_f64(const azp_barrier_args* args, void* stream);
+/* BarrierEvaluator::valid(global_box): 1 when the barrier lies inside the box
+ * (src/HarmonicBarrier.h:126-130 throws "Barrier position is invalid" otherwise). */
+int azp_harmonic_barrier_valid(int geometry, int scalar_bits, double location, const azp_box* box);
+
 /* Uniform(-1,1) value the DPD evaluator draws for a pair (host side; same code as the kernel).
  * Exposes the RNG keying of src/DPDPairEvaluatorGeneralWeight.h:213-233 for parity tests. */
 double azp_dpd_alpha(int scalar_bits, uint32_t seed, uint32_t tag_i, uint32_t tag_j, uint64_t timestep);

@@ -147,6 +147,11 @@ class Oracle:
         lib.oracle_min_image.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                          ctypes.c_int, ctypes.c_void_p]
         lib.oracle_min_image.restype = None
+        lib.oracle_barrier.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_uint32, ctypes.c_void_p,
+                                       ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int]
+        lib.oracle_barrier.restype = ctypes.c_int
         lib.oracle_nlist.argtypes = [ctypes.c_int, ctypes.c_uint32, ctypes.c_void_p,
                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                      ctypes.c_uint32, ctypes.c_void_p, ctypes.c_int,
@@ -290,6 +295,29 @@ class Oracle:
                               pd.ctypes.data, ntypes, rlsq.ctypes.data, int(half),
                               n_neigh.ctypes.data, head.ctypes.data, nlist.ctypes.data, nt, n_rows)
         return n_neigh, nlist, head
+
+    # ---- external harmonic barrier (reference src/HarmonicBarrier.h:149-175) ---------------
+    def barrier_forces(self, geometry, location, pos, params, L, tilt=(0, 0, 0),
+                       periodic=(1, 1, 1), check_valid=True):
+        """geometry: "planar" | "spherical"; params: (ntypes, 2) array of {k, offset}.
+        Returns dict(force (N,4), virial (6,N)); raises RuntimeError("Barrier position is
+        invalid") like the reference when the barrier lies outside the box."""
+        pos = np.ascontiguousarray(pos, dtype=self.dtype)
+        par = np.ascontiguousarray(params, dtype=self.dtype).reshape(-1, 2)
+        N = pos.shape[0]
+        Ld = np.asarray(L, dtype=np.float64)
+        td = np.asarray(tilt, dtype=np.float64)
+        pd = np.asarray(periodic, dtype=np.int32)
+        force = np.zeros((N, 4), dtype=self.dtype)
+        virial = np.full((6, max(N, 1)), 7.0, dtype=self.dtype)
+        g = {"planar": 0, "spherical": 1}[geometry]
+        rc = self.lib.oracle_barrier(g, float(location), N, pos.ctypes.data, par.shape[0],
+                                     par.ctypes.data, Ld.ctypes.data, td.ctypes.data,
+                                     pd.ctypes.data, force.ctypes.data, virial.ctypes.data,
+                                     virial.shape[1], int(check_valid))
+        if rc != 0:
+            raise RuntimeError("Barrier position is invalid")
+        return dict(force=force, virial=virial[:, :N])
 
     # ---- force loops ---------------------------------------------------------------------
     def _args(self, pos, n_neigh, nlist, head, L, tilt, periodic, ntypes, rcut, ron, mode,

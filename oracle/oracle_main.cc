@@ -8,10 +8,15 @@
 //                                            (never copied) against oracle/hoomd_stub
 // Both are driven by the same restated HOOMD host loops (driver_loops.h). All four export the same
 // C symbols; oracle/oracle.py picks one by (kind, precision).
+#include <cmath>
+#include <cstring>
+
 #include "driver_loops.h"
 #include "nlist_cpu.h"
 
 #ifdef ORACLE_USE_REFERENCE
+#include "PlanarBarrierEvaluator.h"
+#include "SphericalBarrierEvaluator.h"
 #include "AnisoPairEvaluatorTwoPatchMorse.h"
 #include "DPDPairEvaluatorGeneralWeight.h"
 #include "PairEvaluatorColloid.h"
@@ -268,6 +273,141 @@ static PairArgs<S> convert(const OracleArgs* o)
     return a;
     }
 
+// ---- external harmonic barrier -------------------------------------------------------------------
+#ifdef ORACLE_USE_REFERENCE
+template<class T>
+static int barrier_loop(int geometry, T location, uint32_t N, const T* pos, uint32_t ntypes, const T* params, const double* L, const double* tilt, const int32_t* periodic, T* force, T* virial, uint64_t pitch, bool check_valid)
+    {
+    hoomd::BoxDim box((T)L[0], (T)L[1], (T)L[2], (T)tilt[0], (T)tilt[1], (T)tilt[2]);
+    box.setPeriodic(periodic[0], periodic[1], periodic[2]);
+    auto run = [&](auto evaluator) -> int
+    {
+        if (check_valid && !evaluator.valid(box))
+            return 1;
+        for (uint32_t i = 0; i < N; ++i)
+            {
+            hoomd::Scalar3 p = hoomd::make_scalar3(pos[4 * i], pos[4 * i + 1], pos[4 * i + 2]);
+            uint32_t type;
+            if (sizeof(T) == 4)
+                memcpy(&type, &pos[4 * i + 3], 4);
+            else
+                {
+                uint64_t t64;
+                memcpy(&t64, &pos[4 * i + 3], 8);
+                type = (uint32_t)t64;
+                }
+            hoomd::int3 img = hoomd::make_int3(0, 0, 0);
+            box.wrap(p, img);
+            const hoomd::Scalar4 f = evaluator(p, params[2 * type], params[2 * type + 1]);
+            force[4 * i] = f.x, force[4 * i + 1] = f.y, force[4 * i + 2] = f.z, force[4 * i + 3] = f.w;
+            }
+        if (virial)
+            for (int r = 0; r < 6; ++r)
+                for (uint32_t i = 0; i < N; ++i)
+                    virial[r * pitch + i] = T(0);
+        return 0;
+    };
+    if (geometry == 0)
+        return run(hoomd::azplugins::PlanarBarrierEvaluator(location));
+    return run(hoomd::azplugins::SphericalBarrierEvaluator(location));
+    }
+#else
+// own restatement of src/PlanarBarrierEvaluator.h:37-51,54-59, src/SphericalBarrierEvaluator.h:36-53,
+// 56-62 and of HOOMD's BoxDim::wrap / makeCoordinates / getNearestPlaneDistance
+template<class T>
+static int barrier_loop(int geometry, T location, uint32_t N, const T* pos, uint32_t ntypes, const T* params, const double* L, const double* tilt, const int32_t* periodic, T* force, T* virial, uint64_t pitch, bool check_valid)
+    {
+    const T Lx = T(L[0]), Ly = T(L[1]), Lz = T(L[2]);
+    const T xy = T(tilt[0]), xz = T(tilt[1]), yz = T(tilt[2]);
+    const T lox = -Lx / T(2.0), loy = -Ly / T(2.0), loz = -Lz / T(2.0);
+    const T hix = lox + Lx, hiy = loy + Ly, hiz = loz + Lz;
+    if (check_valid)
+        {
+        if (geometry == 0)
+            {
+            const T lo = loy + yz * loz, hi = hiy + yz * hiz;
+            if (!(location >= lo && location < hi))
+                return 1;
+            }
+        else
+            {
+            const T term = xy * yz - xz;
+            const T dx = Lx / std::sqrt(T(1.0) + xy * xy + term * term);
+            const T dy = Ly / std::sqrt(T(1.0) + yz * yz);
+            const T two_R = T(2.0) * location;
+            if (!(location >= T(0.0) && dx >= two_R && dy >= two_R && Lz >= two_R))
+                return 1;
+            }
+        }
+    for (uint32_t i = 0; i < N; ++i)
+        {
+        T x = pos[4 * i], y = pos[4 * i + 1], z = pos[4 * i + 2];
+        uint32_t type;
+        if (sizeof(T) == 4)
+            memcpy(&type, &pos[4 * i + 3], 4);
+        else
+            {
+            uint64_t t64;
+            memcpy(&t64, &pos[4 * i + 3], 8);
+            type = (uint32_t)t64;
+            }
+        if (periodic[2])
+            {
+            if (z >= hiz)
+                z -= Lz, y -= Lz * yz, x -= Lz * xz;
+            else if (z < loz)
+                z += Lz, y += Lz * yz, x += Lz * xz;
+            }
+        if (periodic[1])
+            {
+            const T ty = yz * z;
+            if (y >= hiy + ty)
+                y -= Ly, x -= Ly * xy;
+            else if (y < loy + ty)
+                y += Ly, x += Ly * xy;
+            }
+        if (periodic[0])
+            {
+            const T tx = (xz - xy * yz) * z + xy * y;
+            if (x >= hix + tx)
+                x -= Lx;
+            else if (x < lox + tx)
+                x += Lx;
+            }
+        const T k = params[2 * type], offset = params[2 * type + 1];
+        T fx = 0, fy = 0, fz = 0, e = 0;
+        if (geometry == 0)
+            {
+            const T dy = y - (location + offset);
+            if (dy > T(0.0))
+                {
+                const T f = -k * dy;
+                fy = f;
+                e = T(-0.5) * f * dy;
+                }
+            }
+        else
+            {
+            const T r = std::sqrt(x * x + y * y + z * z);
+            const T dr = r - (location + offset);
+            if (dr > T(0.0))
+                {
+                const T k_dr = k * dr;
+                const T c = -(k_dr / r);
+                fx = c * x, fy = c * y, fz = c * z;
+                e = T(0.5) * k_dr * dr;
+                }
+            }
+        force[4 * i] = fx, force[4 * i + 1] = fy, force[4 * i + 2] = fz, force[4 * i + 3] = e;
+        }
+    if (virial)
+        for (int r = 0; r < 6; ++r)
+            for (uint32_t i = 0; i < N; ++i)
+                virial[r * pitch + i] = T(0);
+    return 0;
+    }
+#endif
+
 extern "C"
     {
     int oracle_scalar_size()
@@ -494,6 +634,31 @@ extern "C"
         else
             min_image_host(b, x, y, z);
         v[0] = x, v[1] = y, v[2] = z;
+        }
+
+    // External harmonic barrier: restatement of HarmonicBarrier<Evaluator>::computeForces
+    // (reference src/HarmonicBarrier.h:149-175): per particle wrap into the global box, evaluate,
+    // overwrite force; the virial is zeroed. geometry 0 = planar (y = location), 1 = spherical.
+    // Returns 0, or 1 when the barrier position is invalid (reference :126-130 throws).
+    int oracle_barrier(int geometry,
+                       double location,
+                       uint32_t N,
+                       const void* pos_,
+                       uint32_t ntypes,
+                       const void* params_,
+                       const double* L,
+                       const double* tilt,
+                       const int32_t* periodic,
+                       void* force_,
+                       void* virial_,
+                       uint64_t virial_pitch,
+                       int check_valid)
+        {
+        const S* pos = static_cast<const S*>(pos_);
+        const S* params = static_cast<const S*>(params_); // {k, offset} per type
+        S* force = static_cast<S*>(force_);
+        S* virial = static_cast<S*>(virial_);
+        return barrier_loop<S>(geometry, S(location), N, pos, ntypes, params, L, tilt, periodic, force, virial, virial_pitch, check_valid != 0);
         }
 
     // HOOMD-layout neighbour list on the CPU (nlist_cpu.h); pass 0 counts, pass 1 fills
