@@ -54,6 +54,24 @@ class AzpBarrierArgs(ctypes.Structure):
 BARRIER_PLANAR, BARRIER_SPHERICAL = 0, 1
 
 
+class AzpWallArgs(ctypes.Structure):
+    _fields_ = [
+        ("d_force", ctypes.c_void_p),
+        ("d_virial", ctypes.c_void_p),
+        ("virial_pitch", ctypes.c_uint64),
+        ("d_pos", ctypes.c_void_p),
+        ("d_params", ctypes.c_void_p),
+        ("d_walls", ctypes.c_void_p),
+        ("N", ctypes.c_uint32),
+        ("ntypes", ctypes.c_uint32),
+        ("block_size", ctypes.c_uint32),
+        ("_pad", ctypes.c_uint32),
+    ]
+
+
+WALL_COLLOID, WALL_LJ93 = 0, 1
+
+
 class AzpPairArgs(ctypes.Structure):
     _fields_ = [
         ("d_force", ctypes.c_void_p),
@@ -130,6 +148,10 @@ EXPORTED_SYMBOLS = (
     "azp_harmonic_barrier_f32",
     "azp_harmonic_barrier_f64",
     "azp_harmonic_barrier_valid",
+    "azp_wall_forces_f32",
+    "azp_wall_forces_f64",
+    "azp_wall_param_size",
+    "azp_walls_size",
     "azp_dpd_alpha",
     "azp_philox4x32_10",
     "azp_nlist_cell_dim",
@@ -185,6 +207,14 @@ def _load():
         fn.restype = i32
     lib.azp_harmonic_barrier_valid.argtypes = [i32, i32, ctypes.c_double, ctypes.POINTER(AzpBox)]
     lib.azp_harmonic_barrier_valid.restype = i32
+    for sfx in ("_f32", "_f64"):
+        fn = getattr(lib, "azp_wall_forces" + sfx)
+        fn.argtypes = [i32, ctypes.POINTER(AzpWallArgs), vp]
+        fn.restype = i32
+    lib.azp_wall_param_size.argtypes = [i32, i32]
+    lib.azp_wall_param_size.restype = i32
+    lib.azp_walls_size.argtypes = [i32]
+    lib.azp_walls_size.restype = i32
     lib.azp_dpd_alpha.argtypes = [i32, u32, u32, u32, ctypes.c_uint64]
     lib.azp_dpd_alpha.restype = ctypes.c_double
     lib.azp_philox4x32_10.argtypes = [vp, vp, vp]

@@ -207,6 +207,45 @@ int azp_harmonic_barrier_f64(const azp_barrier_args* args, void* stream);
  * (src/HarmonicBarrier.h:126-130 throws "Barrier position is invalid" otherwise). */
 int azp_harmonic_barrier_valid(int geometry, int scalar_bits, double location, const azp_box* box);
 
+/* Wall potentials wall.Colloid / wall.LJ93. Replaces
+ *   hoomd::md::kernel::gpu_compute_potential_external_forces<EvaluatorWalls<E>>(args, d_params, d_field)
+ * as instantiated by reference src/PotentialExternalWallGPUKernel.cu.inc:13-34 for
+ * E = WallEvaluatorColloid (src/WallEvaluatorColloid.h) and WallEvaluatorLJ93
+ * (src/WallEvaluatorLJ93.h). Layouts (S = float | double, all fields S unless noted):
+ *   d_params[ntypes]: Colloid {c_1 = A sigma^6 / 7560, c_2 = A / 6, a, rcutsq, rextrap}
+ *                     LJ93    {sigma_3, A, rcutsq, rextrap}         (azp_wall_param_size bytes each)
+ *   d_walls: { uint32 n_spheres, n_cylinders, n_planes, pad;
+ *              spheres[20]   {r, origin[3], int32 inside, int32 open};
+ *              cylinders[20] {r, origin[3], axis[3] (unit), int32 inside, int32 open};
+ *              planes[60]    {origin[3], normal[3] (unit), int32 open, int32 pad} }  (azp_walls_size bytes)
+ * rextrap must be 0 (the extrapolated mode of HOOMD's EvaluatorWalls is not built). Energy is
+ * always shifted at r_cut, the virial is F_a * pos_b, as HOOMD's wall loop does. */
+enum azp_wall_evaluator
+    {
+    AZP_WALL_COLLOID = 0,
+    AZP_WALL_LJ93 = 1
+    };
+#define AZP_MAX_SPHERE_WALLS 20
+#define AZP_MAX_CYLINDER_WALLS 20
+#define AZP_MAX_PLANE_WALLS 60
+typedef struct azp_wall_args
+    {
+    void* d_force;        /* Scalar4[N], overwritten */
+    void* d_virial;       /* Scalar[6 * virial_pitch], overwritten; may be NULL */
+    uint64_t virial_pitch;
+    const void* d_pos;    /* Scalar4[N] */
+    const void* d_params; /* per type, see above */
+    const void* d_walls;  /* wall list, see above */
+    uint32_t N;
+    uint32_t ntypes;
+    uint32_t block_size;  /* 0 = library default (256); multiple of 32, <= 256 */
+    uint32_t _pad;
+    } azp_wall_args;
+int azp_wall_forces_f32(int evaluator, const azp_wall_args* args, void* stream);
+int azp_wall_forces_f64(int evaluator, const azp_wall_args* args, void* stream);
+int azp_wall_param_size(int evaluator, int scalar_bits);
+int azp_walls_size(int scalar_bits);
+
 /* Uniform(-1,1) value the DPD evaluator draws for a pair (host side; same code as the kernel).
  * Exposes the RNG keying of src/DPDPairEvaluatorGeneralWeight.h:213-233 for parity tests. */
 double azp_dpd_alpha(int scalar_bits, uint32_t seed, uint32_t tag_i, uint32_t tag_j, uint64_t timestep);

@@ -147,6 +147,11 @@ class Oracle:
         lib.oracle_min_image.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                          ctypes.c_int, ctypes.c_void_p]
         lib.oracle_min_image.restype = None
+        lib.oracle_wall.argtypes = [ctypes.c_int, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p,
+                                    ctypes.c_uint32, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p,
+                                    ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                    ctypes.c_uint64]
+        lib.oracle_wall.restype = ctypes.c_int
         lib.oracle_barrier.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_uint32, ctypes.c_void_p,
                                        ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p,
                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
@@ -295,6 +300,29 @@ class Oracle:
                               pd.ctypes.data, ntypes, rlsq.ctypes.data, int(half),
                               n_neigh.ctypes.data, head.ctypes.data, nlist.ctypes.data, nt, n_rows)
         return n_neigh, nlist, head
+
+    # ---- wall potentials (reference src/WallEvaluator*.h under HOOMD's wall loop) -----------
+    def wall_forces(self, evaluator, pos, params, spheres=(), cylinders=(), planes=()):
+        """evaluator "Colloid" (params rows {c_1, c_2, a, rcutsq, rextrap}) or "LJ93"
+        ({sigma_3, A, rcutsq, rextrap}); walls: spheres (r, origin3, inside, open), cylinders
+        (r, origin3, unit axis3, inside, open), planes (origin3, unit normal3, open).
+        Returns dict(force (N,4), virial (6,N))."""
+        pos = np.ascontiguousarray(pos, dtype=self.dtype)
+        par = np.ascontiguousarray(params, dtype=self.dtype)
+        N = pos.shape[0]
+        sph = np.ascontiguousarray(np.asarray(spheres, dtype=np.float64).reshape(-1, 6))
+        cyl = np.ascontiguousarray(np.asarray(cylinders, dtype=np.float64).reshape(-1, 9))
+        pla = np.ascontiguousarray(np.asarray(planes, dtype=np.float64).reshape(-1, 7))
+        force = np.zeros((N, 4), dtype=self.dtype)
+        virial = np.zeros((6, max(N, 1)), dtype=self.dtype)
+        ev = {"Colloid": 0, "LJ93": 1}[evaluator]
+        rc = self.lib.oracle_wall(ev, N, pos.ctypes.data, par.ctypes.data, sph.shape[0],
+                                  sph.ctypes.data, cyl.shape[0], cyl.ctypes.data, pla.shape[0],
+                                  pla.ctypes.data, force.ctypes.data, virial.ctypes.data,
+                                  virial.shape[1])
+        if rc != 0:
+            raise ValueError("unknown wall evaluator")
+        return dict(force=force, virial=virial[:, :N])
 
     # ---- external harmonic barrier (reference src/HarmonicBarrier.h:149-175) ---------------
     def barrier_forces(self, geometry, location, pos, params, L, tilt=(0, 0, 0),

@@ -15,6 +15,8 @@
 #include "nlist_cpu.h"
 
 #ifdef ORACLE_USE_REFERENCE
+#include "WallEvaluatorColloid.h"
+#include "WallEvaluatorLJ93.h"
 #include "PlanarBarrierEvaluator.h"
 #include "SphericalBarrierEvaluator.h"
 #include "AnisoPairEvaluatorTwoPatchMorse.h"
@@ -271,6 +273,205 @@ static PairArgs<S> convert(const OracleArgs* o)
     a.torque = static_cast<S*>(o->torque);
     a.nthreads = o->nthreads;
     return a;
+    }
+
+// ---- wall potentials -----------------------------------------------------------------------------
+// Evaluators: the reference's own headers (ref build) or the restatement below (port build).
+// The wall loop restates HOOMD's EvaluatorWalls / WallData (not in the reference tree): see
+// azplugins_b200/csrc/wall_kernels.cu for the semantics kept.
+#ifdef ORACLE_USE_REFERENCE
+template<class T> struct WallLJ93
+    {
+    ref::WallParametersLJ93 p;
+    WallLJ93(const T* q)
+        {
+        p.sigma_3 = q[0];
+        p.A = q[1];
+        }
+    bool eval(T rsq, T rcutsq, T& fdr, T& eng) const
+        {
+        ref::WallEvaluatorLJ93 e(rsq, rcutsq, p);
+        return e.evalForceAndEnergy(fdr, eng, true);
+        }
+    };
+template<class T> struct WallColloid
+    {
+    ref::WallParametersColloid p;
+    WallColloid(const T* q)
+        {
+        p.c_1 = q[0];
+        p.c_2 = q[1];
+        p.a = q[2];
+        }
+    bool eval(T rsq, T rcutsq, T& fdr, T& eng) const
+        {
+        ref::WallEvaluatorColloid e(rsq, rcutsq, p);
+        return e.evalForceAndEnergy(fdr, eng, true);
+        }
+    };
+#else
+// restated from src/WallEvaluatorLJ93.h:93-132 and src/WallEvaluatorColloid.h:104-175
+template<class T> struct WallLJ93
+    {
+    T lj1, lj2;
+    WallLJ93(const T* q)
+        {
+        lj1 = (T(2.0) / T(15.0)) * q[1] * q[0] * q[0] * q[0];
+        lj2 = q[1] * q[0];
+        }
+    bool eval(T rsq, T rcutsq, T& fdr, T& eng) const
+        {
+        if (!(rsq < rcutsq && lj1 != 0))
+            return false;
+        T r2inv = T(1.0) / rsq;
+        T r3inv = r2inv * std::sqrt(r2inv);
+        T r6inv = r3inv * r3inv;
+        fdr = r2inv * r3inv * (T(9.0) * lj1 * r6inv - T(3.0) * lj2);
+        eng = r3inv * (lj1 * r6inv - lj2);
+        T rcut2inv = T(1.0) / rcutsq;
+        T rcut3inv = rcut2inv * std::sqrt(rcut2inv);
+        T rcut6inv = rcut3inv * rcut3inv;
+        eng -= rcut3inv * (lj1 * rcut6inv - lj2);
+        return true;
+        }
+    };
+template<class T> struct WallColloid
+    {
+    T c_1, c_2, a;
+    WallColloid(const T* q) : c_1(q[0]), c_2(q[1]), a(q[2]) { }
+    template<bool force> T potential(T& fdr, T rsq) const
+        {
+        T r = std::sqrt(rsq);
+        T arinv = a / r;
+        T rma = T(1.0) / (r - a);
+        T rpa = T(1.0) / (r + a);
+        T r2a2 = rma * rpa;
+        T rma2 = rma * rma;
+        T rma6 = rma2 * rma2 * rma2;
+        T rpa2 = rpa * rpa;
+        T rpa6 = rpa2 * rpa2 * rpa2;
+        if (force)
+            {
+            T arinv8 = T(8.0) * arinv;
+            fdr = T(6.0) * c_1 * ((arinv8 - T(1.0)) * rma2 * rma6 + (arinv8 + T(1.0)) * rpa2 * rpa6);
+            fdr -= c_2 * (T(4.0) * a * a * arinv * r2a2 * r2a2);
+            }
+        T a7 = T(7.0) * a;
+        T energy = c_1 * ((a7 - r) * rma * rma6 + (a7 + r) * rpa * rpa6);
+        energy -= c_2 * (T(2.0) * a * r * r2a2 + std::log(rpa / rma));
+        return energy;
+        }
+    bool eval(T rsq, T rcutsq, T& fdr, T& eng) const
+        {
+        if (!(rsq < rcutsq && c_1 != 0 && a > 0))
+            return false;
+        eng = potential<true>(fdr, rsq);
+        T unused;
+        eng -= potential<false>(unused, rcutsq);
+        return true;
+        }
+    };
+#endif
+
+template<class T, class E>
+static void wall_loop(uint32_t N, const T* pos, uint32_t nparam, const T* params, uint32_t ns, const double* sph, uint32_t nc, const double* cyl, uint32_t np, const double* pla, T* force, T* virial, uint64_t pitch)
+    {
+    auto side = [](T d, T r, bool inside, bool open)
+    { return open ? ((d < r && inside) || (d > r && !inside)) : ((d <= r && inside) || (d >= r && !inside)); };
+    for (uint32_t i = 0; i < N; ++i)
+        {
+        const T x = pos[4 * i], y = pos[4 * i + 1], z = pos[4 * i + 2];
+        uint32_t type;
+        if (sizeof(T) == 4)
+            memcpy(&type, &pos[4 * i + 3], 4);
+        else
+            {
+            uint64_t t64;
+            memcpy(&t64, &pos[4 * i + 3], 8);
+            type = (uint32_t)t64;
+            }
+        const T* q = params + (size_t)nparam * type;
+        const E ev(q);
+        const T rcutsq = q[nparam - 2];
+        T fx = 0, fy = 0, fz = 0, energy = 0;
+        auto add_wall = [&](T dx, T dy, T dz)
+        {
+            const T rx = -dx, ry = -dy, rz = -dz;
+            const T rsq = rx * rx + ry * ry + rz * rz;
+            T fdr = 0, eng = 0;
+            if (ev.eval(rsq, rcutsq, fdr, eng))
+                {
+                if (!std::isfinite(fdr))
+                    fdr = 0, eng = 0;
+                fx += rx * fdr, fy += ry * fdr, fz += rz * fdr;
+                energy += eng;
+                }
+        };
+        for (uint32_t k = 0; k < ns; ++k)
+            {
+            const double* w = sph + 6 * k;
+            const T r = T(w[0]), tx = x - T(w[1]), ty = y - T(w[2]), tz = z - T(w[3]);
+            const bool inside = w[4] != 0, open = w[5] != 0;
+            const T rxyz = std::sqrt(tx * tx + ty * ty + tz * tz);
+            if (rxyz > 0)
+                {
+                if (side(rxyz, r, inside, open))
+                    {
+                    const T s = r / rxyz - T(1.0);
+                    add_wall(s * tx, s * ty, s * tz);
+                    }
+                }
+            else if (inside)
+                add_wall(r, 0, 0);
+            }
+        for (uint32_t k = 0; k < nc; ++k)
+            {
+            const double* w = cyl + 9 * k;
+            const T r = T(w[0]), tx = x - T(w[1]), ty = y - T(w[2]), tz = z - T(w[3]);
+            const T ax = T(w[4]), ay = T(w[5]), az = T(w[6]);
+            const bool inside = w[7] != 0, open = w[8] != 0;
+            const T along = tx * ax + ty * ay + tz * az;
+            const T qx = tx - along * ax, qy = ty - along * ay, qz = tz - along * az;
+            const T rxy = std::sqrt(qx * qx + qy * qy + qz * qz);
+            if (rxy > 0)
+                {
+                if (side(rxy, r, inside, open))
+                    {
+                    const T s = r / rxy - T(1.0);
+                    add_wall(s * qx, s * qy, s * qz);
+                    }
+                }
+            else if (inside)
+                {
+                T ux = 1, uy = 0, uz = 0;
+                if (std::fabs(ax) > T(0.9))
+                    ux = 0, uy = 1;
+                const T d = ux * ax + uy * ay + uz * az;
+                ux -= d * ax, uy -= d * ay, uz -= d * az;
+                const T n = r / std::sqrt(ux * ux + uy * uy + uz * uz);
+                add_wall(n * ux, n * uy, n * uz);
+                }
+            }
+        for (uint32_t k = 0; k < np; ++k)
+            {
+            const double* w = pla + 7 * k;
+            const T ox = T(w[0]), oy = T(w[1]), oz = T(w[2]), nx = T(w[3]), ny = T(w[4]), nz = T(w[5]);
+            const bool open = w[6] != 0;
+            const T d = (nx * x + ny * y + nz * z) - (nx * ox + ny * oy + nz * oz);
+            if (open ? (d > 0) : (d >= 0))
+                add_wall(-d * nx, -d * ny, -d * nz);
+            }
+        force[4 * i] = fx, force[4 * i + 1] = fy, force[4 * i + 2] = fz, force[4 * i + 3] = energy;
+        if (virial)
+            {
+            virial[0 * pitch + i] = fx * x;
+            virial[1 * pitch + i] = fx * y;
+            virial[2 * pitch + i] = fx * z;
+            virial[3 * pitch + i] = fy * y;
+            virial[4 * pitch + i] = fy * z;
+            virial[5 * pitch + i] = fz * z;
+            }
+        }
     }
 
 // ---- external harmonic barrier -------------------------------------------------------------------
@@ -634,6 +835,32 @@ extern "C"
         else
             min_image_host(b, x, y, z);
         v[0] = x, v[1] = y, v[2] = z;
+        }
+
+    // Wall potentials (evaluator 0 = Colloid {c_1, c_2, a, rcutsq, rextrap}, 1 = LJ93 {sigma_3, A,
+    // rcutsq, rextrap} per type); walls as double arrays: spheres [r, o3, inside, open],
+    // cylinders [r, o3, axis3 (unit), inside, open], planes [o3, n3 (unit), open]
+    int oracle_wall(int evaluator,
+                    uint32_t N,
+                    const void* pos,
+                    const void* params,
+                    uint32_t ns,
+                    const double* sph,
+                    uint32_t nc,
+                    const double* cyl,
+                    uint32_t np,
+                    const double* pla,
+                    void* force,
+                    void* virial,
+                    uint64_t pitch)
+        {
+        if (evaluator == 0)
+            wall_loop<S, WallColloid<S>>(N, static_cast<const S*>(pos), 5, static_cast<const S*>(params), ns, sph, nc, cyl, np, pla, static_cast<S*>(force), static_cast<S*>(virial), pitch);
+        else if (evaluator == 1)
+            wall_loop<S, WallLJ93<S>>(N, static_cast<const S*>(pos), 4, static_cast<const S*>(params), ns, sph, nc, cyl, np, pla, static_cast<S*>(force), static_cast<S*>(virial), pitch);
+        else
+            return 1;
+        return 0;
         }
 
     // External harmonic barrier: restatement of HarmonicBarrier<Evaluator>::computeForces
