@@ -257,7 +257,20 @@ class SliceScheduler:
         self.peer_halo = None
         if transport == "peer":
             # move the exchanged arrays into symmetric memory; the State keeps views of them
-            self.peer_halo = PeerHalo(plan, exchange_arrays, group)
+            try:
+                self.peer_halo = PeerHalo(plan, exchange_arrays, group)
+            except Exception as exc:  # no peer access / symmetric memory on this system
+                import warnings
+
+                warnings.warn("peer-memory halo unavailable (%s: %s); using the NCCL transport"
+                              % (type(exc).__name__, exc))
+            # every rank must take the same transport
+            ok = torch.tensor([1 if self.peer_halo is not None else 0], device=state.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok.item()) == 0:
+                self.peer_halo = None
+                self.transport = transport = "nccl"
+        if self.peer_halo is not None:
             for name in ("pos", "vel", "orientation"):
                 for old, new in zip(exchange_arrays, self.peer_halo.arrays):
                     if getattr(state, name) is old:
@@ -273,7 +286,7 @@ class SliceScheduler:
         self._packed = torch.cuda.Event()
         self._step_done = torch.cuda.Event()
         self._step_done.record()
-        if transport == "peer":
+        if self.peer_halo is not None:
             self.launches_per_step = len(pots) + len(self.exchange_arrays)
         else:
             self.launches_per_step = len(pots) * ((1 if plan.interior_rows.numel() else 0)

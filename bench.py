@@ -408,7 +408,7 @@ def run_b200(args):
                                     % (4e-6 * n_bar * n_local),
                        "parallelism": "1 GPU" if not multi else
                        "%d particle slices, %s (%.1f MB/step/rank)"
-                       % (world, "halo pushed over NVLink peer memory" if args.transport == "peer"
+                       % (world, "halo pushed over NVLink peer memory" if sched.transport == "peer"
                           else "NCCL halo exchange", exchange_bytes / 1e6)},
             "roofline": roofline, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
