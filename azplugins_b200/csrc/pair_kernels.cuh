@@ -382,12 +382,30 @@ template<class E_, class S_, bool XPLOR, bool VIRIAL, int NTM_> struct IsoFamily
         types.begin_row(ti, a.ntypes);
         }
 
-    AZP_D void pair(const KernelArgs<S>& a, const RowGeometry<S>& g, unsigned int, const Vec4<S>& pj)
+    // What is left of a neighbour once its gathered position has been consumed: the pipelined
+    // loop computes the heads of a trip, re-issues the gathers into the same registers, then
+    // runs the bodies (no register rotation between trips).
+    struct Head
         {
         S dx, dy, dz;
-        g.displacement(a.box, pj, dx, dy, dz);
+        unsigned int tj;
+        };
+    AZP_D Head head(const KernelArgs<S>& a, const RowGeometry<S>& g, const Vec4<S>& pj) const
+        {
+        Head h;
+        g.displacement(a.box, pj, h.dx, h.dy, h.dz);
+        h.tj = NTM == 1 ? 0u : scalar_as_uint(pj.w);
+        return h;
+        }
+    AZP_D void pair(const KernelArgs<S>& a, const RowGeometry<S>& g, unsigned int, const Vec4<S>& pj)
+        {
+        body(head(a, g, pj));
+        }
+    AZP_D void body(const Head& h)
+        {
+        const S dx = h.dx, dy = h.dy, dz = h.dz;
+        const unsigned int tj = h.tj;
         const S rsq = fma(dz, dz, fma(dy, dy, dx * dx));
-        const unsigned int tj = NTM == 1 ? 0u : scalar_as_uint(pj.w);
         const S rcutsq = types.rcutsq(tj);
         const bool inside = rsq < rcutsq;
         S force_divr = S(0), pair_eng = S(0);
@@ -745,6 +763,28 @@ AZP_D auto pair_dispatch(Fam&, const KernelArgs<S>&, const RowGeometry<S>&, unsi
     -> typename std::enable_if<Fam::QUEUE>::type
     {
     }
+struct NoHead
+    {
+    };
+template<class Fam, class S>
+AZP_D auto head_dispatch(Fam& fam, const KernelArgs<S>& a, const RowGeometry<S>& g, const Vec4<S>& pj)
+    -> typename std::enable_if<Fam::PIPE == 2, typename Fam::Head>::type
+    {
+    return fam.head(a, g, pj);
+    }
+template<class Fam, class S>
+AZP_D auto head_dispatch(Fam&, const KernelArgs<S>&, const RowGeometry<S>&, const Vec4<S>&)
+    -> typename std::enable_if<Fam::PIPE != 2, NoHead>::type
+    {
+    return NoHead();
+    }
+template<class Fam, class H> AZP_D auto body_dispatch(Fam& fam, const H& h) -> typename std::enable_if<Fam::PIPE == 2>::type
+    {
+    fam.body(h);
+    }
+template<class Fam, class H> AZP_D auto body_dispatch(Fam&, const H&) -> typename std::enable_if<Fam::PIPE != 2>::type
+    {
+    }
 template<class Fam, class S>
 AZP_D auto scan_dispatch(Fam& fam, const KernelArgs<S>& a, const RowGeometry<S>& g, unsigned int j, const Vec4<S>& pj)
     -> typename std::enable_if<Fam::QUEUE>::type
@@ -831,7 +871,10 @@ AZP_D void process_row(Fam& fam,
     // Software pipeline. PIPE = 2: the index vector is loaded two trips ahead (it streams from
     // HBM: ~1 us) and the four position gathers one trip ahead (L1/L2), so a lane always has one
     // nlist load and four gathers in flight while it does the math of the current vector --
-    // best for the cheap isotropic evaluators. PIPE = 0: load, gather, compute in program order
+    // best for the cheap isotropic evaluators. A trip first consumes the four gathered positions
+    // (heads: displacement + type, 4 registers each), re-issues the gathers into the same
+    // registers, then runs the four bodies as one branch-free block: no register rotation
+    // (15 MOVs per trip less than copying the positions aside; 0.292 -> 0.280 ms on C2). PIPE = 0: load, gather, compute in program order
     // with the smallest register footprint -- best for the heavy DPD / anisotropic evaluators,
     // which hide latency with occupancy instead (measured).
     unsigned int v = v_begin + lane;
@@ -852,8 +895,10 @@ AZP_D void process_row(Fam& fam,
         while (v < v_end)
             {
             const unsigned int v1 = v + tpp, v2 = v1 + tpp;
-            const uint4 j = j_cur;
-            const Vec4<S> q0 = p0, q1 = p1, q2 = p2, q3 = p3;
+            const auto h0 = head_dispatch(fam, a, g, p0);
+            const auto h1 = head_dispatch(fam, a, g, p1);
+            const auto h2 = head_dispatch(fam, a, g, p2);
+            const auto h3 = head_dispatch(fam, a, g, p3);
             if (v1 < v_end)
                 {
                 j_cur = j_nxt;
@@ -864,10 +909,10 @@ AZP_D void process_row(Fam& fam,
                 if (v2 < v_end)
                     j_nxt = __ldg(base4 + v2);
                 }
-            pair_dispatch(fam, a, g, j.x, q0);
-            pair_dispatch(fam, a, g, j.y, q1);
-            pair_dispatch(fam, a, g, j.z, q2);
-            pair_dispatch(fam, a, g, j.w, q3);
+            body_dispatch(fam, h0);
+            body_dispatch(fam, h1);
+            body_dispatch(fam, h2);
+            body_dispatch(fam, h3);
             v = v1;
             }
         }
