@@ -47,10 +47,10 @@ METRIC = "pair_force_particle_steps_per_s"
 UNIT = "particle-steps/s"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the
 # committed `ncu --set full` capture of this command (profiles/); None until captured.
-NCU_TRAFFIC_BYTES = {"C2": 614.26e6}  # profiles/r01_c2_ncu_full_v5_summary.csv (577.12 + 37.14 MB)
+NCU_TRAFFIC_BYTES = {"C2": 614.97e6}  # profiles/r01_c2_ncu_full_v7_summary.csv (578.60 + 36.37 MB)
 # warp instructions executed per launch of the same capture (smsp__inst_executed.sum): the kernel
 # is instruction-issue bound, not HBM bound, so the issue floor is reported beside the HBM roofline
-NCU_WARP_INSTRUCTIONS = {"C2": 226.94e6}
+NCU_WARP_INSTRUCTIONS = {"C2": 217.95e6}
 SM_COUNT, SCHEDULERS_PER_SM = 148, 4
 
 
