@@ -390,18 +390,18 @@ template<class E_, class S_, bool XPLOR, bool VIRIAL, int NTM_> struct IsoFamily
         S dx, dy, dz;
         unsigned int tj;
         };
-    AZP_D Head head(const KernelArgs<S>& a, const RowGeometry<S>& g, const Vec4<S>& pj) const
+    AZP_D Head head(const KernelArgs<S>& a, const RowGeometry<S>& g, unsigned int, const Vec4<S>& pj) const
         {
         Head h;
         g.displacement(a.box, pj, h.dx, h.dy, h.dz);
         h.tj = NTM == 1 ? 0u : scalar_as_uint(pj.w);
         return h;
         }
-    AZP_D void pair(const KernelArgs<S>& a, const RowGeometry<S>& g, unsigned int, const Vec4<S>& pj)
+    AZP_D void pair(const KernelArgs<S>& a, const RowGeometry<S>& g, unsigned int j, const Vec4<S>& pj)
         {
-        body(head(a, g, pj));
+        body(a, head(a, g, j, pj));
         }
-    AZP_D void body(const Head& h)
+    AZP_D void body(const KernelArgs<S>&, const Head& h)
         {
         const S dx = h.dx, dy = h.dy, dz = h.dz;
         const unsigned int tj = h.tj;
@@ -634,6 +634,9 @@ template<class E_, class S_, bool VIRIAL, int NTM_> struct AnisoFamily
     typedef S_ S;
     typedef typename E::cache_type Cache;
     static constexpr int NTM = NTM_;
+    // measured on C5: the software pipeline of the isotropic family (PIPE = 2) needs 99
+    // registers here and is 50 % slower (0.69 vs 0.46 ms per 4 M particles) than hiding the
+    // latency with occupancy (58 registers, 8 CTAs per SM)
     static constexpr int PIPE = 0;
     // measured on C5 (51 % of the entries accepted, 16.6 per row): deferring the accepted pairs
     // (AcceptQueue) saves 11 % of the instructions but lengthens the dependent memory chains and
@@ -767,22 +770,24 @@ struct NoHead
     {
     };
 template<class Fam, class S>
-AZP_D auto head_dispatch(Fam& fam, const KernelArgs<S>& a, const RowGeometry<S>& g, const Vec4<S>& pj)
+AZP_D auto head_dispatch(Fam& fam, const KernelArgs<S>& a, const RowGeometry<S>& g, unsigned int j, const Vec4<S>& pj)
     -> typename std::enable_if<Fam::PIPE == 2, typename Fam::Head>::type
     {
-    return fam.head(a, g, pj);
+    return fam.head(a, g, j, pj);
     }
 template<class Fam, class S>
-AZP_D auto head_dispatch(Fam&, const KernelArgs<S>&, const RowGeometry<S>&, const Vec4<S>&)
+AZP_D auto head_dispatch(Fam&, const KernelArgs<S>&, const RowGeometry<S>&, unsigned int, const Vec4<S>&)
     -> typename std::enable_if<Fam::PIPE != 2, NoHead>::type
     {
     return NoHead();
     }
-template<class Fam, class H> AZP_D auto body_dispatch(Fam& fam, const H& h) -> typename std::enable_if<Fam::PIPE == 2>::type
+template<class Fam, class S, class H>
+AZP_D auto body_dispatch(Fam& fam, const KernelArgs<S>& a, const H& h) -> typename std::enable_if<Fam::PIPE == 2>::type
     {
-    fam.body(h);
+    fam.body(a, h);
     }
-template<class Fam, class H> AZP_D auto body_dispatch(Fam&, const H&) -> typename std::enable_if<Fam::PIPE != 2>::type
+template<class Fam, class S, class H>
+AZP_D auto body_dispatch(Fam&, const KernelArgs<S>&, const H&) -> typename std::enable_if<Fam::PIPE != 2>::type
     {
     }
 template<class Fam, class S>
@@ -895,10 +900,10 @@ AZP_D void process_row(Fam& fam,
         while (v < v_end)
             {
             const unsigned int v1 = v + tpp, v2 = v1 + tpp;
-            const auto h0 = head_dispatch(fam, a, g, p0);
-            const auto h1 = head_dispatch(fam, a, g, p1);
-            const auto h2 = head_dispatch(fam, a, g, p2);
-            const auto h3 = head_dispatch(fam, a, g, p3);
+            const auto h0 = head_dispatch(fam, a, g, j_cur.x, p0);
+            const auto h1 = head_dispatch(fam, a, g, j_cur.y, p1);
+            const auto h2 = head_dispatch(fam, a, g, j_cur.z, p2);
+            const auto h3 = head_dispatch(fam, a, g, j_cur.w, p3);
             if (v1 < v_end)
                 {
                 j_cur = j_nxt;
@@ -909,10 +914,10 @@ AZP_D void process_row(Fam& fam,
                 if (v2 < v_end)
                     j_nxt = __ldg(base4 + v2);
                 }
-            body_dispatch(fam, h0);
-            body_dispatch(fam, h1);
-            body_dispatch(fam, h2);
-            body_dispatch(fam, h3);
+            body_dispatch(fam, a, h0);
+            body_dispatch(fam, a, h1);
+            body_dispatch(fam, a, h2);
+            body_dispatch(fam, a, h3);
             v = v1;
             }
         }
@@ -953,11 +958,21 @@ AZP_D void process_row(Fam& fam,
         // warp-wide heavy round runs whenever some lane could not take another trip.
         const unsigned int full = 0xffffffffu;
         bool more = v < v_end;
+        // the index vector (the HBM stream: the longest latency of a trip) is loaded one trip
+        // ahead; 4 registers, C4 0.378 -> 0.360 ms per 2 M particles. (The same prefetch in the
+        // in-place loop of the anisotropic family makes ptxas use 83 registers instead of 58
+        // and is 20 % slower, so that loop loads its indices just in time; prefetching the
+        // position gathers across the heavy rounds as well costs 96 registers and 24 %.)
+        uint4 j_nxt = make_uint4(0u, 0u, 0u, 0u);
+        if (more)
+            j_nxt = __ldg(base4 + v);
         while (__any_sync(full, more))
             {
             if (more)
                 {
-                const uint4 j = __ldg(base4 + v);
+                const uint4 j = j_nxt;
+                if (v + tpp < v_end)
+                    j_nxt = __ldg(base4 + v + tpp);
                 const Vec4<S> q0 = load4(a.pos, j.x);
                 const Vec4<S> q1 = load4(a.pos, j.y);
                 const Vec4<S> q2 = load4(a.pos, j.z);
