@@ -7,8 +7,8 @@ Host-side mirror of the reference plugin surface (``pair``, ``external``, ``wall
 """
 
 from . import _lib  # noqa: F401  (fails loudly when the CUDA extension is not built)
-from . import external, kernels, nlist, pair, wall
+from . import external, kernels, md, nlist, pair, wall
 from .box import Box
 from .state import State
 
-__all__ = ["Box", "State", "external", "kernels", "nlist", "pair", "wall"]
+__all__ = ["Box", "State", "external", "kernels", "md", "nlist", "pair", "wall"]

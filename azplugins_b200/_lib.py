@@ -54,6 +54,24 @@ class AzpBarrierArgs(ctypes.Structure):
 BARRIER_PLANAR, BARRIER_SPHERICAL = 0, 1
 
 
+MD_MAX_FORCES = 8
+
+
+class AzpMdArgs(ctypes.Structure):
+    _fields_ = [
+        ("d_pos", ctypes.c_void_p),
+        ("d_vel", ctypes.c_void_p),
+        ("d_accel", ctypes.c_void_p),
+        ("d_image", ctypes.c_void_p),
+        ("d_net_force", ctypes.c_void_p),
+        ("d_forces", ctypes.c_void_p * MD_MAX_FORCES),
+        ("n_forces", ctypes.c_uint32),
+        ("N", ctypes.c_uint32),
+        ("box", AzpBox),
+        ("dt", ctypes.c_double),
+    ]
+
+
 class AzpWallArgs(ctypes.Structure):
     _fields_ = [
         ("d_force", ctypes.c_void_p),
@@ -152,6 +170,10 @@ EXPORTED_SYMBOLS = (
     "azp_wall_forces_f64",
     "azp_wall_param_size",
     "azp_walls_size",
+    "azp_nve_step_one_f32",
+    "azp_nve_step_one_f64",
+    "azp_nve_step_two_f32",
+    "azp_nve_step_two_f64",
     "azp_dpd_alpha",
     "azp_philox4x32_10",
     "azp_nlist_cell_dim",
@@ -215,6 +237,11 @@ def _load():
     lib.azp_wall_param_size.restype = i32
     lib.azp_walls_size.argtypes = [i32]
     lib.azp_walls_size.restype = i32
+    for name in ("azp_nve_step_one", "azp_nve_step_two"):
+        for sfx in ("_f32", "_f64"):
+            fn = getattr(lib, name + sfx)
+            fn.argtypes = [ctypes.POINTER(AzpMdArgs), vp]
+            fn.restype = i32
     lib.azp_dpd_alpha.argtypes = [i32, u32, u32, u32, ctypes.c_uint64]
     lib.azp_dpd_alpha.restype = ctypes.c_double
     lib.azp_philox4x32_10.argtypes = [vp, vp, vp]

@@ -246,6 +246,31 @@ int azp_wall_forces_f64(int evaluator, const azp_wall_args* args, void* stream);
 int azp_wall_param_size(int evaluator, int scalar_bits);
 int azp_walls_size(int scalar_bits);
 
+/* Velocity-Verlet (NVE) steps either side of the force path: what HOOMD's
+ * md.methods.ConstantVolume does around the force computes the reference plugs in (usage:
+ * reference src/pytest/test_pair.py:325-327). HOOMD is not in the reference tree: restated as
+ *   step one: v += a dt/2; x += v dt; wrap into the (orthorhombic) box, counting images
+ *   step two: F = sum of d_forces[0..n_forces); a = F/m (m = vel.w); v += a dt/2
+ * IEEE arithmetic without FMA contraction (a numpy restatement is bit-exact). */
+#define AZP_MD_MAX_FORCES 8
+typedef struct azp_md_args
+    {
+    void* d_pos;       /* Scalar4[N] (step one) */
+    void* d_vel;       /* Scalar4[N] (vx, vy, vz, mass) */
+    void* d_accel;     /* Scalar4[N] (ax, ay, az, 0): read by step one, written by step two */
+    int32_t* d_image;  /* int32[3 N] or NULL (step one) */
+    void* d_net_force; /* Scalar4[N] or NULL: sum of the forces, energy in .w (step two) */
+    const void* d_forces[AZP_MD_MAX_FORCES]; /* Scalar4[N] each (step two) */
+    uint32_t n_forces;
+    uint32_t N;
+    azp_box box;
+    double dt;
+    } azp_md_args;
+int azp_nve_step_one_f32(const azp_md_args* args, void* stream);
+int azp_nve_step_one_f64(const azp_md_args* args, void* stream);
+int azp_nve_step_two_f32(const azp_md_args* args, void* stream);
+int azp_nve_step_two_f64(const azp_md_args* args, void* stream);
+
 /* Uniform(-1,1) value the DPD evaluator draws for a pair (host side; same code as the kernel).
  * Exposes the RNG keying of src/DPDPairEvaluatorGeneralWeight.h:213-233 for parity tests. */
 double azp_dpd_alpha(int scalar_bits, uint32_t seed, uint32_t tag_i, uint32_t tag_j, uint64_t timestep);
