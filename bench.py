@@ -435,6 +435,13 @@ def main():
     os.dup2(2, 1)
     args = parse()
     if args.impl == "reference":
+        # the CPU arm uses every host core it may run on; torchrun exports OMP_NUM_THREADS=1,
+        # which must be overridden before the OpenMP runtime is loaded
+        try:
+            cores = len(os.sched_getaffinity(0))
+        except AttributeError:
+            cores = os.cpu_count() or 1
+        os.environ["OMP_NUM_THREADS"] = str(cores)
         run_reference(args)
     else:
         run_b200(args)
