@@ -322,11 +322,13 @@ extern "C"
             cudaEventDestroy(e0);
             return (int)err;
             }
-        const uint32_t blocks[] = {64, 128, 256, 512};
+        // multiples of 32 that divide the register file differently (e.g. 160 threads x 79
+        // registers keeps 25 warps per SM resident where 128 keeps 24)
+        const uint32_t blocks[] = {64, 96, 128, 160, 192, 256, 512};
         float best = -1.0f;
         uint32_t bb = 128, bt = 8;
         int rc = 0;
-        for (uint32_t bi = 0; bi < 4 && rc == 0; ++bi)
+        for (uint32_t bi = 0; bi < sizeof(blocks) / sizeof(blocks[0]) && rc == 0; ++bi)
             for (uint32_t tpp = 1; tpp <= 32 && rc == 0; tpp <<= 1)
                 {
                 azp_pair_args t = *a;
