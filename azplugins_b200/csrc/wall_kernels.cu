@@ -12,8 +12,9 @@
 //   * in the active space the evaluator sees rsq = |drv|^2 with energy_shift = true, and
 //     F += -drv * force_divr, U += pair_eng (a non-finite force_divr counts as zero);
 //   * virial = F_a * pos_b (xx, xy, xz, yy, yz, zz);
-//   * r_extrap > 0 (linear extrapolation inside the wall) is rejected by the host layer: the
-//     reference's own tests never use it and its exact branch order could not be pinned.
+//   * r_extrap > 0: closer to the wall than r_extrap, or on its wrong side, the potential is
+//     evaluated at r_extrap and continued linearly (add_wall_extrap). The reference's own tests
+//     never use this mode: restated from HOOMD's published behaviour, parity-unpinned.
 // One-body streaming kernel, HBM-bound like the harmonic barrier (barrier_kernels.cu): 16 B in,
 // 16 + 24 B out per particle; the wall list and the per-type parameters sit in shared memory.
 #include "../../include/azp_b200.h"
@@ -172,6 +173,47 @@ template<class S, class E> AZP_D void add_wall(const E& ev, S rcutsq, S dx, S dy
         }
     }
 
+// One wall in HOOMD's extrapolated mode (r_extrap > 0): beyond r_extrap from the wall, in the
+// active space, the potential as is; closer -- or on the wrong side of the wall -- the potential
+// evaluated AT r_extrap and continued linearly with the force it has there:
+//   U = U(r_e) + F(r_e) (r_e -/+ r),  F = F(r_e) along the wall normal, pointing into the active space.
+// (nx, ny, nz) is the unit direction used when the particle sits exactly on the wall.
+template<class S, class E>
+AZP_D void add_wall_extrap(const E& ev, S rcutsq, S rextrap, bool in_active, S dx, S dy, S dz, S nx, S ny, S nz, S& fx, S& fy, S& fz, S& energy)
+    {
+    const S rextrapsq = mul(rextrap, rextrap);
+    const S rsq = add(add(mul(dx, dx), mul(dy, dy)), mul(dz, dz));
+    if (in_active && rsq >= rextrapsq)
+        {
+        add_wall(ev, rcutsq, dx, dy, dz, fx, fy, fz, energy);
+        return;
+        }
+    S r = root(rsq);
+    if (rsq == S(0))
+        {
+        in_active = true;
+        dx = nx, dy = ny, dz = nz;
+        }
+    else
+        {
+        const S rinv = div(S(1.0), r);
+        dx = mul(dx, rinv), dy = mul(dy, rinv), dz = mul(dz, rinv);
+        }
+    r = in_active ? sub(rextrap, r) : add(rextrap, r);
+    const S scale = in_active ? rextrap : -rextrap;
+    dx = mul(dx, scale), dy = mul(dy, scale), dz = mul(dz, scale);
+    const S rx = -dx, ry = -dy, rz = -dz;
+    S force_divr = S(0), pair_eng = S(0);
+    if (ev.eval(rextrapsq, rcutsq, force_divr, pair_eng))
+        {
+        pair_eng = add(pair_eng, mul(mul(force_divr, rextrap), r));
+        energy = add(energy, pair_eng);
+        fx = add(fx, mul(rx, force_divr));
+        fy = add(fy, mul(ry, force_divr));
+        fz = add(fz, mul(rz, force_divr));
+        }
+    }
+
 template<class S, class E>
 __global__ void __launch_bounds__(256) wall_kernel(S* __restrict__ force,
                                                     S* __restrict__ virial,
@@ -202,6 +244,7 @@ __global__ void __launch_bounds__(256) wall_kernel(S* __restrict__ force,
     const unsigned int type = scalar_as_uint(p.w);
     const TypeParams<S, E> tp = s_params[type < ntypes ? type : 0u];
     const E ev(tp.params);
+    const bool extrap = tp.rextrap > S(0);
     S fx = S(0), fy = S(0), fz = S(0), energy = S(0);
 
     for (unsigned int k = 0; k < walls->n_spheres; ++k)
@@ -222,7 +265,15 @@ __global__ void __launch_bounds__(256) wall_kernel(S* __restrict__ force,
             in_active = w.inside != 0;
             dx = w.r, dy = S(0), dz = S(0);
             }
-        if (in_active)
+        if (extrap)
+            {
+            // on-wall direction = from the particle towards the wall as seen from the active
+            // space: radially outwards for an inside wall, inwards otherwise
+            const S sgn = w.inside ? S(1) : S(-1);
+            const S inv = rxyz > S(0) ? div(sgn, rxyz) : S(0);
+            add_wall_extrap(ev, tp.rcutsq, tp.rextrap, in_active, dx, dy, dz, rxyz > S(0) ? mul(tx, inv) : sgn, mul(ty, inv), mul(tz, inv), fx, fy, fz, energy);
+            }
+        else if (in_active)
             add_wall(ev, tp.rcutsq, dx, dy, dz, fx, fy, fz, energy);
         }
     for (unsigned int k = 0; k < walls->n_cylinders; ++k)
@@ -235,11 +286,15 @@ __global__ void __launch_bounds__(256) wall_kernel(S* __restrict__ force,
         const S rxy = root(add(add(mul(qx, qx), mul(qy, qy)), mul(qz, qz)));
         if (rxy > S(0))
             {
-            if (active_side(rxy, w.r, w.inside, w.open))
+            const bool in_active = active_side(rxy, w.r, w.inside, w.open);
+            const S s = sub(div(w.r, rxy), S(1.0));
+            if (extrap)
                 {
-                const S s = sub(div(w.r, rxy), S(1.0));
-                add_wall(ev, tp.rcutsq, mul(s, qx), mul(s, qy), mul(s, qz), fx, fy, fz, energy);
+                const S inv = div(w.inside ? S(1) : S(-1), rxy);
+                add_wall_extrap(ev, tp.rcutsq, tp.rextrap, in_active, mul(s, qx), mul(s, qy), mul(s, qz), mul(qx, inv), mul(qy, inv), mul(qz, inv), fx, fy, fz, energy);
                 }
+            else if (in_active)
+                add_wall(ev, tp.rcutsq, mul(s, qx), mul(s, qy), mul(s, qz), fx, fy, fz, energy);
             }
         else if (w.inside)
             {
@@ -250,7 +305,10 @@ __global__ void __launch_bounds__(256) wall_kernel(S* __restrict__ force,
             const S d = add(add(mul(ux, w.ax), mul(uy, w.ay)), mul(uz, w.az));
             ux = sub(ux, mul(d, w.ax)), uy = sub(uy, mul(d, w.ay)), uz = sub(uz, mul(d, w.az));
             const S n = div(w.r, root(add(add(mul(ux, ux), mul(uy, uy)), mul(uz, uz))));
-            add_wall(ev, tp.rcutsq, mul(n, ux), mul(n, uy), mul(n, uz), fx, fy, fz, energy);
+            if (extrap)
+                add_wall_extrap(ev, tp.rcutsq, tp.rextrap, true, mul(n, ux), mul(n, uy), mul(n, uz), S(0), S(0), S(0), fx, fy, fz, energy);
+            else
+                add_wall(ev, tp.rcutsq, mul(n, ux), mul(n, uy), mul(n, uz), fx, fy, fz, energy);
             }
         }
     for (unsigned int k = 0; k < walls->n_planes; ++k)
@@ -259,7 +317,9 @@ __global__ void __launch_bounds__(256) wall_kernel(S* __restrict__ force,
         const S d = sub(add(add(mul(w.nx, p.x), mul(w.ny, p.y)), mul(w.nz, p.z)),
                         add(add(mul(w.nx, w.ox), mul(w.ny, w.oy)), mul(w.nz, w.oz)));
         const bool in_active = w.open ? (d > S(0)) : (d >= S(0));
-        if (in_active)
+        if (extrap)
+            add_wall_extrap(ev, tp.rcutsq, tp.rextrap, in_active, mul(-d, w.nx), mul(-d, w.ny), mul(-d, w.nz), -w.nx, -w.ny, -w.nz, fx, fy, fz, energy);
+        else if (in_active)
             add_wall(ev, tp.rcutsq, mul(-d, w.nx), mul(-d, w.ny), mul(-d, w.nz), fx, fy, fz, energy);
         }
 

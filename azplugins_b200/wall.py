@@ -6,8 +6,9 @@ keys ``A``, ``a``, ``sigma``, ``r_cut``, ``r_extrap``; C++ class names ``WallsPo
 ``Cylinder``, ``Plane``), on top of the C ABI ``azp_wall_forces_f32/_f64``
 (``include/azp_b200.h``). The evaluator arithmetic is the reference's
 (``src/WallEvaluatorColloid.h``, ``src/WallEvaluatorLJ93.h``); the wall loop restates HOOMD's
-``EvaluatorWalls`` (not in the reference tree). ``r_extrap > 0`` (HOOMD's extrapolated mode) is
-not built and raises. CUDA only: there is no CPU fallback.
+``EvaluatorWalls`` (not in the reference tree), including its extrapolated mode (``r_extrap > 0``:
+closer to a wall than ``r_extrap`` the potential continues linearly). CUDA only: there is no CPU
+fallback.
 """
 
 import ctypes
@@ -160,11 +161,11 @@ class WallPotential:
             if name not in self.params:
                 raise ValueError("params not set for particle type %s" % name)
             p = self.params[name]
-            if p["r_extrap"] != 0.0:
-                raise NotImplementedError("r_extrap > 0 (extrapolated wall mode) is not built")
+            if p["r_extrap"] < 0.0:
+                raise ValueError("r_extrap must be >= 0")
             S = np.dtype(dtype).type
             rc = S(p["r_cut"])
-            rows.append(list(self._row(p, S)) + [rc * rc, S(0.0)])
+            rows.append(list(self._row(p, S)) + [rc * rc, S(p["r_extrap"])])
         return np.asarray(rows, dtype=dtype)
 
     def attach(self, state):

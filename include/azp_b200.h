@@ -218,8 +218,9 @@ int azp_harmonic_barrier_valid(int geometry, int scalar_bits, double location, c
  *              spheres[20]   {r, origin[3], int32 inside, int32 open};
  *              cylinders[20] {r, origin[3], axis[3] (unit), int32 inside, int32 open};
  *              planes[60]    {origin[3], normal[3] (unit), int32 open, int32 pad} }  (azp_walls_size bytes)
- * rextrap must be 0 (the extrapolated mode of HOOMD's EvaluatorWalls is not built). Energy is
- * always shifted at r_cut, the virial is F_a * pos_b, as HOOMD's wall loop does. */
+ * rextrap > 0 selects HOOMD's extrapolated mode (linear continuation closer than rextrap to a wall
+ * or behind it). Energy is always shifted at r_cut, the virial is F_a * pos_b, as HOOMD's wall
+ * loop does. */
 enum azp_wall_evaluator
     {
     AZP_WALL_COLLOID = 0,

@@ -394,6 +394,8 @@ static void wall_loop(uint32_t N, const T* pos, uint32_t nparam, const T* params
         const E ev(q);
         const T rcutsq = q[nparam - 2];
         T fx = 0, fy = 0, fz = 0, energy = 0;
+        const T rextrap = q[nparam - 1];
+        const bool extrap = rextrap > 0;
         auto add_wall = [&](T dx, T dy, T dz)
         {
             const T rx = -dx, ry = -dy, rz = -dz;
@@ -407,6 +409,38 @@ static void wall_loop(uint32_t N, const T* pos, uint32_t nparam, const T* params
                 energy += eng;
                 }
         };
+        // HOOMD's extrapolated mode (restated): see wall_kernels.cu add_wall_extrap
+        auto add_wall_extrap = [&](bool in_active, T dx, T dy, T dz, T nx, T ny, T nz)
+        {
+            const T rextrapsq = rextrap * rextrap;
+            const T rsq = dx * dx + dy * dy + dz * dz;
+            if (in_active && rsq >= rextrapsq)
+                {
+                add_wall(dx, dy, dz);
+                return;
+                }
+            T r = std::sqrt(rsq);
+            if (rsq == 0)
+                {
+                in_active = true;
+                dx = nx, dy = ny, dz = nz;
+                }
+            else
+                {
+                const T rinv = T(1.0) / r;
+                dx *= rinv, dy *= rinv, dz *= rinv;
+                }
+            r = in_active ? rextrap - r : rextrap + r;
+            const T scale = in_active ? rextrap : -rextrap;
+            dx *= scale, dy *= scale, dz *= scale;
+            T fdr = 0, eng = 0;
+            if (ev.eval(rextrapsq, rcutsq, fdr, eng))
+                {
+                eng = eng + fdr * rextrap * r;
+                energy += eng;
+                fx += -dx * fdr, fy += -dy * fdr, fz += -dz * fdr;
+                }
+        };
         for (uint32_t k = 0; k < ns; ++k)
             {
             const double* w = sph + 6 * k;
@@ -415,12 +449,18 @@ static void wall_loop(uint32_t N, const T* pos, uint32_t nparam, const T* params
             const T rxyz = std::sqrt(tx * tx + ty * ty + tz * tz);
             if (rxyz > 0)
                 {
-                if (side(rxyz, r, inside, open))
+                const bool act = side(rxyz, r, inside, open);
+                const T s = r / rxyz - T(1.0);
+                if (extrap)
                     {
-                    const T s = r / rxyz - T(1.0);
-                    add_wall(s * tx, s * ty, s * tz);
+                    const T inv = (inside ? T(1) : T(-1)) / rxyz;
+                    add_wall_extrap(act, s * tx, s * ty, s * tz, tx * inv, ty * inv, tz * inv);
                     }
+                else if (act)
+                    add_wall(s * tx, s * ty, s * tz);
                 }
+            else if (extrap)
+                add_wall_extrap(inside, r, 0, 0, inside ? T(1) : T(-1), 0, 0);
             else if (inside)
                 add_wall(r, 0, 0);
             }
@@ -435,11 +475,15 @@ static void wall_loop(uint32_t N, const T* pos, uint32_t nparam, const T* params
             const T rxy = std::sqrt(qx * qx + qy * qy + qz * qz);
             if (rxy > 0)
                 {
-                if (side(rxy, r, inside, open))
+                const bool act = side(rxy, r, inside, open);
+                const T s = r / rxy - T(1.0);
+                if (extrap)
                     {
-                    const T s = r / rxy - T(1.0);
-                    add_wall(s * qx, s * qy, s * qz);
+                    const T inv = (inside ? T(1) : T(-1)) / rxy;
+                    add_wall_extrap(act, s * qx, s * qy, s * qz, qx * inv, qy * inv, qz * inv);
                     }
+                else if (act)
+                    add_wall(s * qx, s * qy, s * qz);
                 }
             else if (inside)
                 {
@@ -449,7 +493,10 @@ static void wall_loop(uint32_t N, const T* pos, uint32_t nparam, const T* params
                 const T d = ux * ax + uy * ay + uz * az;
                 ux -= d * ax, uy -= d * ay, uz -= d * az;
                 const T n = r / std::sqrt(ux * ux + uy * uy + uz * uz);
-                add_wall(n * ux, n * uy, n * uz);
+                if (extrap)
+                    add_wall_extrap(true, n * ux, n * uy, n * uz, 0, 0, 0);
+                else
+                    add_wall(n * ux, n * uy, n * uz);
                 }
             }
         for (uint32_t k = 0; k < np; ++k)
@@ -458,7 +505,10 @@ static void wall_loop(uint32_t N, const T* pos, uint32_t nparam, const T* params
             const T ox = T(w[0]), oy = T(w[1]), oz = T(w[2]), nx = T(w[3]), ny = T(w[4]), nz = T(w[5]);
             const bool open = w[6] != 0;
             const T d = (nx * x + ny * y + nz * z) - (nx * ox + ny * oy + nz * oz);
-            if (open ? (d > 0) : (d >= 0))
+            const bool act = open ? (d > 0) : (d >= 0);
+            if (extrap)
+                add_wall_extrap(act, -d * nx, -d * ny, -d * nz, -nx, -ny, -nz);
+            else if (act)
                 add_wall(-d * nx, -d * ny, -d * nz);
             }
         force[4 * i] = fx, force[4 * i + 1] = fy, force[4 * i + 2] = fz, force[4 * i + 3] = energy;

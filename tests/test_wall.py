@@ -26,12 +26,13 @@ def _kinds():
 def _row(name, p, dtype):
     S = np.dtype(dtype).type
     rc = S(p["r_cut"])
+    re = S(p.get("r_extrap", 0.0))
     if name == "Colloid":
         A, sigma = S(p["A"]), S(p["sigma"])
         s3 = sigma * sigma * sigma
-        return [A * s3 * s3 / S(7560), A / S(6), S(p["a"]), rc * rc, S(0)]
+        return [A * s3 * s3 / S(7560), A / S(6), S(p["a"]), rc * rc, re]
     sigma = S(p["sigma"])
-    return [sigma * sigma * sigma, S(p["A"]), rc * rc, S(0)]
+    return [sigma * sigma * sigma, S(p["A"]), rc * rc, re]
 
 
 @pytest.mark.parametrize("kind", _kinds())
@@ -63,17 +64,39 @@ def _system(rng, N, dtype):
 PARAMS = {"Colloid": [{"A": 100.0, "a": 0.75, "sigma": 1.0, "r_cut": 3.0},
                       {"A": 40.0, "a": 1.25, "sigma": 0.9, "r_cut": 4.0}],
           "LJ93": [{"A": 2.0, "sigma": 1.0, "r_cut": 3.0}, {"A": 0.0, "sigma": 1.2, "r_cut": 2.5}]}
+# the same with HOOMD's extrapolated mode switched on for the first type
+PARAMS_EXTRAP = {"Colloid": [dict(PARAMS["Colloid"][0], r_extrap=1.1), PARAMS["Colloid"][1]],
+                 "LJ93": [dict(PARAMS["LJ93"][0], r_extrap=0.9), PARAMS["LJ93"][1]]}
+
+
+@pytest.mark.parametrize("kind", _kinds())
+@pytest.mark.parametrize("name", ["Colloid", "LJ93"])
+def test_oracle_extrapolated_mode_is_continuous_and_linear(kind, name):
+    """r_extrap > 0: U and F continuous at r_extrap, F constant and U linear closer to (and
+    behind) the wall."""
+    o = oracle.load(kind, np.float64)
+    p = PARAMS_EXTRAP[name][0]
+    re = p["r_extrap"]
+    z = np.array([re + 1e-9, re - 1e-9, 0.5 * re, 0.25 * re, 0.0, -0.3])
+    pos = oracle.make_pos(np.c_[np.zeros_like(z), np.zeros_like(z), z], np.zeros(len(z), int), np.float64)
+    r = o.wall_forces(name, pos, [_row(name, p, np.float64)], planes=[[0, 0, 0, 0, 0, 1, 1]])
+    fz, u = r["force"][:, 2], r["force"][:, 3]
+    assert abs(fz[0] - fz[1]) < 1e-6 * abs(fz[0]) and abs(u[0] - u[1]) < 1e-6 * max(1.0, abs(u[0]))
+    assert np.allclose(fz[1:], fz[1], rtol=1e-12)  # constant force inside r_extrap and behind the wall
+    # U(z) = U(r_e) + F (r_e - z): linear in z with slope -F
+    assert np.allclose(u[2:], u[1] + fz[1] * (re - 1e-9 - z[2:]), rtol=1e-9, atol=1e-9)
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("name", ["Colloid", "LJ93"])
 @pytest.mark.parametrize("wallset", sorted(WALLSETS))
-def test_port_equals_reference_headers(dtype, name, wallset):
+@pytest.mark.parametrize("extrap", [False, True])
+def test_port_equals_reference_headers(dtype, name, wallset, extrap):
     if not oracle.available("ref", 32):
         pytest.skip("oracle/_ref not built")
     xyz, typeid = _system(np.random.default_rng(3), 3000, dtype)
     pos = oracle.make_pos(xyz, typeid, dtype)
-    rows = [_row(name, p, dtype) for p in PARAMS[name]]
+    rows = [_row(name, p, dtype) for p in (PARAMS_EXTRAP if extrap else PARAMS)[name]]
     a = oracle.load("port", dtype).wall_forces(name, pos, rows, **WALLSETS[wallset])
     b = oracle.load("ref", dtype).wall_forces(name, pos, rows, **WALLSETS[wallset])
     assert np.array_equal(a["force"], b["force"], equal_nan=True)
@@ -113,14 +136,15 @@ def test_gpu_known_answers(dtype, name, params, position, energy, fz):
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("name", ["Colloid", "LJ93"])
 @pytest.mark.parametrize("wallset", sorted(WALLSETS))
-def test_gpu_parity_with_oracle(dtype, name, wallset):
+@pytest.mark.parametrize("extrap", [False, True])
+def test_gpu_parity_with_oracle(dtype, name, wallset, extrap):
     import azplugins_b200 as az
 
     xyz, typeid = _system(np.random.default_rng(11), 50021, dtype)
     state = az.State(az.Box.cube(20.0), ["A", "B"], xyz, typeid=typeid, dtype=dtype, device="cuda:0")
     walls = _geometries(WALLSETS[wallset])
     pot = getattr(az.wall, name)(walls=walls)
-    for t, p in zip(["A", "B"], PARAMS[name]):
+    for t, p in zip(["A", "B"], (PARAMS_EXTRAP if extrap else PARAMS)[name]):
         pot.params[t] = p
     pot.attach(state).compute()
     sph, cyl, pla = az.wall.walls_as_arrays(walls)
@@ -152,8 +176,8 @@ def test_gpu_wall_errors():
     pot.attach(state)
     with pytest.raises(ValueError):
         pot.compute()  # params missing
-    pot.params["A"] = dict(A=1.0, sigma=1.0, r_cut=3.0, r_extrap=1.1)
-    with pytest.raises(NotImplementedError):
+    pot.params["A"] = dict(A=1.0, sigma=1.0, r_cut=3.0, r_extrap=-0.1)
+    with pytest.raises(ValueError):
         pot.compute()
     with pytest.raises(ValueError):
         pot.params["A"] = dict(A=1.0, sigma=1.0)
