@@ -72,11 +72,13 @@ class Integrator:
         _lib.check(rc, name)
 
     def _compute_forces(self, compute_virial):
+        from . import pair
+
         ts = self._state.timestep
         for f in self.forces:
-            try:
+            if isinstance(f, pair.Pair):
                 f.compute(timestep=ts, compute_virial=compute_virial)
-            except TypeError:  # one-body potentials take no compute_virial
+            else:  # one-body potentials (external, wall) always fill their virial array
                 f.compute(timestep=ts)
 
     def run(self, steps, compute_virial=False):
