@@ -84,6 +84,22 @@ def _worker(rank, world, port, out):
         halo([lpos, lquat])
         assert np.array_equal(lpos.numpy(), pos[gl]) and np.array_equal(lquat.numpy(), quat[gl])
         assert halo.bytes_per_step([lpos, lquat]) == plan.n_ghost * 2 * 4 * 8
+        # what the NVLink peer push (PeerHalo) addresses: on every receiver, the first ghost row
+        # of every owner's segment, and my particles arriving there in the receiver's ghost order
+        starts = plan.peer_ghost_start
+        assert starts.shape == (world, world)
+        assert starts[rank][rank] >= plan.n_local and (starts[rank] >= plan.n_local).all()
+        for owner in range(world):
+            o, c = int(plan.recv_offsets[owner]), int(plan.recv_counts[owner])
+            assert starts[rank][owner] == plan.n_local + o
+            if c:
+                assert (ids[o:o + c] >= bounds[owner]).all() and (ids[o:o + c] < bounds[owner + 1]).all()
+        for peer in range(world):
+            if peer != rank:
+                # rows I push to `peer` land at starts[peer][rank] ... + send_counts[peer]
+                n_peer_local = int(bounds[peer + 1] - bounds[peer])
+                assert starts[peer][rank] >= n_peer_local
+                assert int(plan.send_counts[peer]) == int(plan.send_idx[peer].numel())
         # a second exchange after the owners moved their particles
         pos2 = pos.copy()
         pos2[:, :3] += 0.01 * np.sin(np.arange(wl.N))[:, None]
