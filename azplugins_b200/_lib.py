@@ -142,6 +142,8 @@ class AzpNlistArgs(ctypes.Structure):
         ("row_offset", ctypes.c_uint32),
         ("n_rows", ctypes.c_uint32),
         ("_pad", ctypes.c_uint32),
+        ("d_capacity", ctypes.c_void_p),
+        ("d_overflow", ctypes.c_void_p),
     ]
 
 

@@ -36,6 +36,8 @@ template<class S> struct NlistArgs
     CellGrid grid;
     unsigned int row_offset;
     unsigned int n_rows;
+    const unsigned int* capacity; // FILL only: reuse of the previous build's row capacities
+    unsigned int* overflow;
     };
 
 template<class S> AZP_D void cell_coords(const BoxDim<S>& b, const CellGrid& g, S x, S y, S z, int c[3])
@@ -94,6 +96,7 @@ template<class S, bool FILL> __global__ void __launch_bounds__(128) nlist_rows(c
     cell_coords(a.box, a.grid, pi.x, pi.y, pi.z, c);
     unsigned int count = 0;
     unsigned int* row = FILL ? a.nlist + a.head_list[r] : nullptr;
+    const unsigned int cap = (FILL && a.capacity) ? a.capacity[r] : 0xffffffffu;
     for (int oz = -a.grid.reach[2]; oz <= a.grid.reach[2]; ++oz)
         for (int oy = -a.grid.reach[1]; oy <= a.grid.reach[1]; ++oy)
             for (int ox = -a.grid.reach[0]; ox <= a.grid.reach[0]; ++ox)
@@ -131,7 +134,7 @@ template<class S, bool FILL> __global__ void __launch_bounds__(128) nlist_rows(c
                     const S rsq = dx * dx + dy * dy + dz * dz;
                     if (rsq < a.rlistsq[index2d(a.ntypes, ti, scalar_as_uint(pj.w))])
                         {
-                        if (FILL)
+                        if (FILL && count < cap)
                             row[count] = j;
                         ++count;
                         }
@@ -139,6 +142,14 @@ template<class S, bool FILL> __global__ void __launch_bounds__(128) nlist_rows(c
                 }
     if (!FILL)
         a.n_neigh[r] = count;
+    else if (a.capacity)
+        {
+        // capacity reuse: the fill is also the count; a row that needed more slots than it has
+        // is truncated and reported (the caller rebuilds with a count pass)
+        a.n_neigh[r] = min(count, cap);
+        if (count > cap)
+            atomicMax(a.overflow, 1u);
+        }
     }
 
 template<class S> static NlistArgs<S> convert(const azp_nlist_args& a)
@@ -166,6 +177,8 @@ template<class S> static NlistArgs<S> convert(const azp_nlist_args& a)
     k.cell_order = a.d_cell_order;
     k.row_offset = a.n_rows ? a.row_offset : 0u;
     k.n_rows = a.n_rows ? a.n_rows : a.N;
+    k.capacity = a.d_capacity;
+    k.overflow = a.d_overflow;
     return k;
     }
 
@@ -225,6 +238,8 @@ template<class S, bool FILL> static int rows(const azp_nlist_args* a, cudaStream
     if (!valid_common(a) || !a->d_n_neigh)
         return (int)cudaErrorInvalidValue;
     if (FILL && (!a->d_head_list || !a->d_nlist))
+        return (int)cudaErrorInvalidValue;
+    if (FILL && a->d_capacity && !a->d_overflow)
         return (int)cudaErrorInvalidValue;
     if (a->N == 0)
         return 0;

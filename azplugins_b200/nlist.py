@@ -106,6 +106,7 @@ class Cell(NeighborList):
         super().__init__(buffer, exclusions, rebuild_check_delay, check_dist, default_r_cut)
         self.deterministic = deterministic
         self.row_align = int(row_align)
+        self.reuse_capacity = True  # skip the count pass while the previous row capacities suffice
 
     def build(self, state, rows=None):
         """Build the list for all particles of ``state`` or, with ``rows=(lo, hi)``, only for the
@@ -155,23 +156,45 @@ class Cell(NeighborList):
             a.d_cell_order = cell_order.data_ptr()
             a.d_n_neigh = n_neigh.data_ptr()
             _lib.check(getattr(_lib.lib, "azp_nlist_bin" + sfx)(ctypes.byref(a), stream), "nlist bin")
-            _lib.check(getattr(_lib.lib, "azp_nlist_count" + sfx)(ctypes.byref(a), stream), "nlist count")
-            # head_list = prefix sum of Nmax[type] (HOOMD's row capacity rule)
-            typeid = particle_typeid(state.pos)[lo:hi]
-            cap = torch.zeros(n_rows, dtype=torch.int64, device=dev)
-            for t in range(nt):
-                sel = typeid == t
-                if bool(sel.any()):
-                    m = int(n_neigh[sel].max())
-                    m = (m + self.row_align - 1) // self.row_align * self.row_align
-                    cap[sel] = m
-            head = torch.cumsum(cap, 0) - cap
-            size = int(cap.sum())
-            self.n_max = int(cap.max().item()) if n_rows else 0
-            nlist = torch.zeros(max(size, 1), dtype=torch.int32, device=dev)
-            a.d_head_list = head.data_ptr()
-            a.d_nlist = nlist.data_ptr()
-            _lib.check(getattr(_lib.lib, "azp_nlist_fill" + sfx)(ctypes.byref(a), stream), "nlist fill")
+            # Capacity reuse (what HOOMD's NeighborList does between builds): when the previous
+            # build had the same rows, fill straight into its row capacities -- the fill counts as
+            # it goes -- and fall back to count + fill only if some row overflowed.
+            prev = getattr(self, "_reuse", None)
+            reused = False
+            if prev is not None and prev["key"] == (n_total, lo, hi, bits) and self.reuse_capacity:
+                head, cap32, size = prev["head"], prev["cap32"], prev["size"]
+                nlist = self.nlist if (self.nlist is not None and self.nlist.numel() == max(size, 1)) \
+                    else torch.zeros(max(size, 1), dtype=torch.int32, device=dev)
+                prev["overflow"].zero_()
+                a.d_head_list = head.data_ptr()
+                a.d_nlist = nlist.data_ptr()
+                a.d_capacity = cap32.data_ptr()
+                a.d_overflow = prev["overflow"].data_ptr()
+                _lib.check(getattr(_lib.lib, "azp_nlist_fill" + sfx)(ctypes.byref(a), stream), "nlist fill")
+                reused = int(prev["overflow"].item()) == 0
+                a.d_capacity = None
+                a.d_overflow = None
+            if not reused:
+                _lib.check(getattr(_lib.lib, "azp_nlist_count" + sfx)(ctypes.byref(a), stream), "nlist count")
+                # head_list = prefix sum of Nmax[type] (HOOMD's row capacity rule)
+                typeid = particle_typeid(state.pos)[lo:hi]
+                cap = torch.zeros(n_rows, dtype=torch.int64, device=dev)
+                for t in range(nt):
+                    sel = typeid == t
+                    if bool(sel.any()):
+                        m = int(n_neigh[sel].max())
+                        m = (m + self.row_align - 1) // self.row_align * self.row_align
+                        cap[sel] = m
+                head = torch.cumsum(cap, 0) - cap
+                size = int(cap.sum())
+                self.n_max = int(cap.max().item()) if n_rows else 0
+                nlist = torch.zeros(max(size, 1), dtype=torch.int32, device=dev)
+                a.d_head_list = head.data_ptr()
+                a.d_nlist = nlist.data_ptr()
+                _lib.check(getattr(_lib.lib, "azp_nlist_fill" + sfx)(ctypes.byref(a), stream), "nlist fill")
+                self._reuse = dict(key=(n_total, lo, hi, bits), head=head, cap32=cap.to(torch.int32),
+                                   size=size, overflow=torch.zeros(1, dtype=torch.int32, device=dev))
+            self.num_reused = getattr(self, "num_reused", 0) + int(reused)
         # rows of ghosts are built too but only the first N rows are consumed
         self.n_neigh, self.nlist, self.head_list, self.size = n_neigh, nlist, head, size
         self._pos_at_build = state.pos.clone()

@@ -303,6 +303,13 @@ typedef struct azp_nlist_args
     uint32_t row_offset;
     uint32_t n_rows;
     uint32_t _pad;
+    /* Optional (azp_nlist_fill only): skip the count pass by reusing the row capacities of the
+     * previous build, as HOOMD does. d_capacity[row] = slots of the row; the fill then writes at
+     * most that many entries, stores the true count in d_n_neigh[row] and raises *d_overflow
+     * (uint32, zeroed by the caller) when a row needed more -- the caller then falls back to
+     * count + fill. NULL = exact fill after the count pass; d_n_neigh is then not written. */
+    const uint32_t* d_capacity;
+    uint32_t* d_overflow;
     } azp_nlist_args;
 
 int azp_nlist_cell_dim(const azp_box* box, double r_list_max, uint32_t dim[3]);

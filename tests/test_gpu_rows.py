@@ -61,3 +61,43 @@ def test_compute_to_host_matches_device_results():
         pot.compute_to_host(hf, hv, chunks=chunks)
         assert torch.equal(hf, f0)
         assert torch.equal(hv, v0)
+
+
+def test_nlist_capacity_reuse_gives_the_same_list():
+    """A rebuild that reuses the previous row capacities (no count pass) yields the same rows as a
+    from-scratch build; an overflowing row falls back to count + fill."""
+    wl = synth.config2(N=30000)
+    state = wl.make_state(dtype=np.float32, device="cuda:0")
+    nl = az.nlist.Cell(buffer=synth.BUFFER)
+    (pot,) = wl.make_potentials(nl)
+    pot.attach(state)
+    nl.build(state)
+    assert nl.num_reused == 0
+    ref = [t.clone() for t in (nl.n_neigh, nl.nlist, nl.head_list)]
+    # small displacements: same capacities suffice
+    g = torch.Generator(device="cuda").manual_seed(1)
+    state.pos[:, :3] += 0.05 * (torch.rand(state.pos[:, :3].shape, device="cuda", generator=g) - 0.5)
+    nl.build(state)
+    assert nl.num_reused == 1
+    reused = [t.clone() for t in (nl.n_neigh, nl.nlist, nl.head_list)]
+    nl.reuse_capacity = False
+    nl.build(state)
+    assert nl.num_reused == 1
+    nn = nl.n_neigh.long()
+    assert torch.equal(reused[0], nl.n_neigh)
+    # same valid entries row by row (capacities, hence heads, may differ)
+    for r in (0, 1, 777, 29999):
+        a = reused[1][int(reused[2][r]):int(reused[2][r]) + int(nn[r])]
+        b = nl.nlist[int(nl.head_list[r]):int(nl.head_list[r]) + int(nn[r])]
+        assert torch.equal(a, b)
+    # overflow: squeeze many particles together so that some rows outgrow their capacity
+    nl.reuse_capacity = True
+    nl.build(state)
+    reused_before = nl.num_reused
+    state.pos[:2000, :3] = state.pos[:1, :3] + 0.3 * torch.rand((2000, 3), device="cuda", generator=g)
+    nl.build(state)
+    assert nl.num_reused == reused_before  # fell back to the count pass
+    assert int(nl.n_neigh.max()) >= 1999
+    pot.compute()
+    torch.cuda.synchronize()
+    del ref

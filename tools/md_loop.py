@@ -46,5 +46,6 @@ torch.cuda.synchronize()
 dt = time.perf_counter() - t0
 e1 = ig.kinetic_energy() + ig.potential_energy()
 print("%s N=%d: %d steps in %.3f s = %.1f time steps/s = %.3e particle-steps/s; %d neighbour-list "
-      "builds; total energy %.6g -> %.6g (fp32)" % (cfg, N, steps, dt, steps / dt, N * steps / dt,
-                                                     nl.num_builds - b0, e0, e1))
+      "builds (%d reused the row capacities); total energy %.6g -> %.6g (fp32)"
+      % (cfg, N, steps, dt, steps / dt, N * steps / dt, nl.num_builds - b0,
+         getattr(nl, "num_reused", 0), e0, e1))
