@@ -122,11 +122,16 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def timed_with_clocks(fn, device_index):
+def timed_with_clocks(fn, device_index, probe=None):
+    """Run `fn` (the timed region) with the clock sampler on; `probe`, if given, then repeats the
+    same load untimed for about a second so that the sampler (one nvidia-smi call per ~0.1 s)
+    sees the clocks under that load more than once -- the timed region itself lasts ~15 ms."""
     sampler = ClockSampler(device_index)
     sampler.start()
     try:
         out = fn()
+        if probe is not None:
+            probe()
     finally:
         sampler.stop_flag.set()
         sampler.join(timeout=2)
@@ -319,7 +324,24 @@ def run_b200(args):
         barrier()
         return e0.elapsed_time(e1)
 
-    ms_total, clocks = timed_with_clocks(timed_region, local_rank)
+    def load_probe():
+        # same step, untimed; a fixed count so that every rank runs the same number of steps
+        # (the multi-GPU step contains device barriers)
+        for _ in range(probe_steps):
+            step()
+        torch.cuda.synchronize()
+
+    # ~1 s of load from the warm-up's own timing (identical on every rank: all-reduced)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    est = torch.tensor([(time.perf_counter() - t0) / 3.0], dtype=torch.float64, device=dev)
+    if multi:
+        dist.all_reduce(est, op=dist.ReduceOp.MAX)
+    probe_steps = int(min(20000, max(10, 1.0 / max(float(est.item()), 1e-6))))
+    ms_total, clocks = timed_with_clocks(timed_region, local_rank, load_probe)
+    clocks["sampled_over"] = "timed region + %d untimed repeats of the same step" % probe_steps
     if multi:
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
