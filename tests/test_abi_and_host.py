@@ -35,7 +35,9 @@ def test_struct_layout_matches_header_sizes():
 
     from azplugins_b200 import _lib
 
-    src = '#include "azp_b200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu\\n", sizeof(azp_box), sizeof(azp_pair_args), sizeof(azp_nlist_args));return 0;}\n'
+    src = ('#include "azp_b200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n", '
+           'sizeof(azp_box), sizeof(azp_pair_args), sizeof(azp_nlist_args), sizeof(azp_barrier_args), '
+           'sizeof(azp_wall_args), sizeof(azp_md_args));return 0;}\n')
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "s.c"), "w").write(src)
         subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "s.c"), "-o",
@@ -43,7 +45,8 @@ def test_struct_layout_matches_header_sizes():
         out = subprocess.run([os.path.join(d, "s")], capture_output=True, text=True, check=True).stdout
     sizes = [int(x) for x in out.split()]
     assert sizes == [ctypes.sizeof(_lib.AzpBox), ctypes.sizeof(_lib.AzpPairArgs),
-                     ctypes.sizeof(_lib.AzpNlistArgs)]
+                     ctypes.sizeof(_lib.AzpNlistArgs), ctypes.sizeof(_lib.AzpBarrierArgs),
+                     ctypes.sizeof(_lib.AzpWallArgs), ctypes.sizeof(_lib.AzpMdArgs)]
 
 
 def test_evaluator_names_and_param_sizes():
@@ -153,8 +156,15 @@ def test_no_cpu_fallback():
     # the product package never imports the oracle
     import sys
 
+    # the one-body potentials and the integrator refuse a CPU state as well
+    bar = az.external.PlanarHarmonicBarrier(location=1.0)
+    wall = az.wall.LJ93(walls=[az.wall.Plane((0, 0, 0), (0, 0, 1))])
+    for obj in (bar, wall, az.md.Integrator(dt=0.001, forces=[bar])):
+        with pytest.raises(_lib.AzpError):
+            obj.attach(state)
     for mod in ("azplugins_b200.pair", "azplugins_b200.kernels", "azplugins_b200.nlist",
-                "azplugins_b200.slices", "azplugins_b200.synth"):
+                "azplugins_b200.slices", "azplugins_b200.synth", "azplugins_b200.external",
+                "azplugins_b200.wall", "azplugins_b200.md"):
         __import__(mod)
         src = open(sys.modules[mod].__file__).read()
         assert "import oracle" not in src and "from oracle" not in src
@@ -176,3 +186,63 @@ def test_synthetic_workloads():
     # Morton order keeps consecutive particles close
     d = np.linalg.norm(np.diff(wl.position, axis=0), axis=1)
     assert np.median(d) < 2.5
+
+
+def test_external_and_wall_host_logic():
+    """API surface of the external / wall mirrors (reference src/external.py, src/wall.py) and the
+    host-side staging: wall-list layout, parameter rows with the reference constructors'
+    roundings, the barrier validity rule."""
+    import azplugins_b200 as az
+    from azplugins_b200 import _lib, wall
+
+    # class-name mapping and parameter schema
+    bar = az.external.SphericalHarmonicBarrier(location=3.0)
+    assert bar.cpp_class_name == "SphericalHarmonicBarrierGPU" and bar.location(7) == 3.0
+    bar.params["A"] = dict(k=10.0, offset=0.5)
+    assert bar.params["A"] == dict(k=10.0, offset=0.5)
+    with pytest.raises(ValueError):
+        bar.params["A"] = dict(k=1.0)
+    ramp = az.external.PlanarHarmonicBarrier(location=lambda t: 5.0 - 0.001 * t)
+    assert ramp.location(1000) == 4.0
+    col = wall.Colloid(walls=[])
+    assert col.cpp_class_name == "WallsPotentialColloidGPU"
+    col.params["A"] = dict(A=1.0, a=1.0, sigma=1.0, r_cut=3.0)
+    assert col.params["A"]["r_extrap"] == 0.0
+    # parameter rows: c_1 = A sigma^6 / 7560, c_2 = A / 6 in Scalar arithmetic (WallEvaluatorColloid.h:36-45)
+    for dtype in (np.float32, np.float64):
+        S = np.dtype(dtype).type
+        row = col.param_table(["A"], dtype)[0]
+        assert row.dtype == dtype and row.shape == (5,)
+        assert row[0] == S(1.0) / S(7560) and row[1] == S(1.0) / S(6) and row[3] == S(9.0)
+        assert col.param_table(["A"], dtype).nbytes == _lib.lib.azp_wall_param_size(_lib.WALL_COLLOID, 8 * row.itemsize)
+        lj = wall.LJ93(walls=[])
+        lj.params["A"] = dict(A=2.0, sigma=1.5, r_cut=2.0, r_extrap=0.5)
+        r2 = lj.param_table(["A"], dtype)[0]
+        assert r2[0] == S(1.5) * S(1.5) * S(1.5) and r2[1] == S(2.0) and r2[2] == S(4.0) and r2[3] == S(0.5)
+        assert lj.param_table(["A"], dtype).nbytes == _lib.lib.azp_wall_param_size(_lib.WALL_LJ93, 8 * row.itemsize)
+        # wall list layout = the library's struct
+        walls = [wall.Sphere(2.0, origin=(1, 2, 3), inside=False), wall.Cylinder(1.5, axis=(0, 0, 2)),
+                 wall.Plane((0, 0, -1), (0, 3, 4), open=False)]
+        blob = wall.pack_walls(walls, dtype)
+        assert len(blob) == _lib.lib.azp_walls_size(8 * row.itemsize)
+        head = np.frombuffer(blob[:16], dtype=np.uint32)
+        assert list(head[:3]) == [1, 1, 1]
+        sph, cyl, pla = wall.walls_as_arrays(walls)
+        assert sph == [[2.0, 1.0, 2.0, 3.0, False, True]] and cyl[0][4:7] == [0.0, 0.0, 1.0]
+        assert np.allclose(pla[0][3:6], [0.0, 0.6, 0.8]) and pla[0][6] is False
+    with pytest.raises(ValueError):
+        wall.pack_walls([wall.Plane((0, 0, 0), (0, 0, 1))] * 61, np.float32)
+    with pytest.raises(ValueError):
+        wall.Plane((0, 0, 0), (0, 0, 0))
+    # barrier validity (PlanarBarrierEvaluator.h:54-59, SphericalBarrierEvaluator.h:56-62)
+    box = az.Box.cube(20.0).to_c()
+    valid = _lib.lib.azp_harmonic_barrier_valid
+    for bits in (32, 64):
+        assert valid(_lib.BARRIER_PLANAR, bits, -10.0, ctypes.byref(box)) == 1
+        assert valid(_lib.BARRIER_PLANAR, bits, 10.0, ctypes.byref(box)) == 0
+        assert valid(_lib.BARRIER_SPHERICAL, bits, 10.0, ctypes.byref(box)) == 1
+        assert valid(_lib.BARRIER_SPHERICAL, bits, 10.01, ctypes.byref(box)) == 0
+        assert valid(_lib.BARRIER_SPHERICAL, bits, -0.1, ctypes.byref(box)) == 0
+    # integrator argument checks
+    with pytest.raises(ValueError):
+        az.md.Integrator(dt=0.001, forces=[bar], methods=[object()])
