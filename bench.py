@@ -174,7 +174,7 @@ def cpu_oracle_rate(wl, target_seconds=8.0, steps=1, warmup=0, quiet=True):
 
     lists = {}
 
-    def run(n_rows):
+    def run(n_rows, nthreads=0):
         if n_rows not in lists:
             lists.clear()
             lists[n_rows] = orc.build_nlist(pos, wl.box.L, rc_max + 0.4, ntypes=nt, n_rows=n_rows)
@@ -185,16 +185,16 @@ def cpu_oracle_rate(wl, target_seconds=8.0, steps=1, warmup=0, quiet=True):
             if name == "TwoPatchMorse":
                 orc.aniso_forces(table, pos, wl.orientation.astype(np.float32), nn, nl, head,
                                  wl.box.L, rc, ntypes=nt, mode=mode, virial=wl.compute_virial,
-                                 N=n_rows)
+                                 N=n_rows, nthreads=nthreads)
             elif name == "DPDGeneralWeight":
                 vel = np.zeros((len(pos), 4), dtype=np.float32)
                 vel[:, :3] = wl.velocity
                 orc.dpd_forces(table, pos, vel, wl.tag, nn, nl, head, wl.box.L, rc, wl.seed,
                                wl.timestep, wl.dt, s["kwargs"]["kT"], ntypes=nt,
-                               virial=wl.compute_virial, N=n_rows)
+                               virial=wl.compute_virial, N=n_rows, nthreads=nthreads)
             else:
                 orc.pair_forces(name, table, pos, nn, nl, head, wl.box.L, rc, ntypes=nt,
-                                mode=mode, virial=wl.compute_virial, N=n_rows)
+                                mode=mode, virial=wl.compute_virial, N=n_rows, nthreads=nthreads)
         return time.perf_counter() - t0
 
     probe_rows = min(wl.N, 20000)
@@ -204,7 +204,17 @@ def cpu_oracle_rate(wl, target_seconds=8.0, steps=1, warmup=0, quiet=True):
         run(n_rows)
     times = [run(n_rows) for _ in range(max(1, steps))]
     t = float(np.median(times))
+    # one thread on the same rows (what a single HOOMD CPU rank does); the list
+    # of the sample is reused, the pass is bounded by taking the probe's rows
+    t1 = run(n_rows, nthreads=1) if n_rows <= 4 * probe_rows else None
+    if t1 is None:
+        lists.clear()
+        t1_rows = probe_rows
+        t1 = run(t1_rows, nthreads=1)
+    else:
+        t1_rows = n_rows
     info = {"value": n_rows / t, "unit": UNIT, "cores": cores, "kind": kind,
+            "value_1_thread": t1_rows / t1,
             "sample": "first %d of %d rows of %s, full neighbour list, fp32, %.2f s per pass "
                       "(HOOMD's CPU classes would use a half list: half the pair evaluations)"
                       % (n_rows, wl.N, wl.name, t)}
