@@ -81,8 +81,20 @@ class Integrator:
             else:  # one-body potentials (external, wall) always fill their virial array
                 f.compute(timestep=ts)
 
-    def run(self, steps, compute_virial=False):
-        """Advance ``steps`` time steps (``sim.run(steps)``)."""
+    def _one_step(self, args, compute_virial):
+        self._call("azp_nve_step_one", args)
+        self._state.timestep += 1
+        self._compute_forces(compute_virial)
+        self._call("azp_nve_step_two", args)
+
+    def run(self, steps, compute_virial=False, graph=False):
+        """Advance ``steps`` time steps (``sim.run(steps)``).
+
+        ``graph=True``: the steps during which the neighbour lists need no displacement check
+        (``rebuild_check_delay`` after a build, HOOMD's own knob) are replayed from a CUDA graph of
+        one step -- three or four kernels per replay instead of as many ctypes launches plus a
+        device-to-host flag read -- which is what bounds small systems. Only for
+        forces that do not depend on the time step (no DPD thermostat, no moving barrier)."""
         st = self._state
         if st is None:
             raise RuntimeError("integrator is not attached to a State")
@@ -94,12 +106,69 @@ class Integrator:
             self._call("azp_nve_step_two", a)
             self._prepared = True
         a = self._args()
-        for _ in range(int(steps)):
-            self._call("azp_nve_step_one", a)
-            st.timestep += 1
-            self._compute_forces(compute_virial)
-            self._call("azp_nve_step_two", a)
+        steps = int(steps)
+        if not graph:
+            for _ in range(steps):
+                self._one_step(a, compute_virial)
+            return self
+        lists = self._graph_lists()
+        done = 0
+        g, g_builds = None, None
+        while done < steps:
+            # a checked step: may rebuild the lists
+            self._one_step(a, compute_virial)
+            done += 1
+            quiet = min([nl.steps_until_check(st) for nl in lists] + [steps - done])
+            # the step after this one must still be un-checked for a replay to be legal
+            quiet = min(quiet - 1, steps - done) if lists else steps - done
+            if quiet <= 0:
+                continue
+            # the graph holds device addresses: capture again only when a rebuild moved a buffer
+            # (rebuilds that reuse the row capacities keep n_neigh / nlist / head_list in place)
+            builds = tuple(t.data_ptr() for nl in lists for t in (nl.n_neigh, nl.nlist, nl.head_list))
+            if g is None or builds != g_builds:
+                g = self._capture(a, compute_virial, lists)
+                g_builds = builds
+            for _ in range(quiet):
+                g.replay()
+            st.timestep += quiet
+            done += quiet
         return self
+
+    def _graph_lists(self):
+        from . import external, pair
+
+        lists = []
+        for f in self.forces:
+            if isinstance(f, pair.DPDGeneralWeight) and type(f) is pair.DPDGeneralWeight:
+                raise ValueError("graph=True needs forces that do not depend on the time step (DPD thermostat)")
+            if isinstance(f, external.HarmonicBarrier) and not isinstance(f.location, external._Constant):
+                raise ValueError("graph=True needs forces that do not depend on the time step (moving barrier)")
+            nl = getattr(f, "nlist", None)
+            if nl is not None and nl not in lists:
+                if nl.n_max > 512:
+                    raise ValueError("graph=True does not cover the long-row pass (rows longer than 512)")
+                lists.append(nl)
+        return lists
+
+    def _capture(self, args, compute_virial, lists):
+        """Record one step (no displacement check: the caller replays it only while none is due)."""
+        st = self._state
+        saved = [(nl, nl.check_dist) for nl in lists]
+        ts = st.timestep
+        for nl, _ in saved:
+            nl.check_dist = False
+        try:
+            with torch.cuda.device(st.device):
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._one_step(args, compute_virial)
+        finally:
+            st.timestep = ts  # capturing records the kernels, it does not run them
+            for nl, flag in saved:
+                nl.check_dist = flag
+        return g
 
     # ---- thermodynamic read-outs (ComputeThermo's quantities) ------------------------------
     def kinetic_energy(self):

@@ -71,12 +71,27 @@ class NeighborList:
         return self
 
     def compute(self, state):
+        """Rebuild when needed (HOOMD ``NeighborList::compute``): never for an adopted list; always
+        when there is none yet; otherwise, once ``rebuild_check_delay`` steps have passed since
+        the last build, when some particle has moved more than half the buffer."""
         if self._external:
             return False
-        if self.n_neigh is None or self._needs_rebuild(state):
+        if self.n_neigh is None:
             self.build(state)
+            self._build_step = state.timestep
+            return True
+        if self.steps_until_check(state) > 0:
+            return False
+        if self._needs_rebuild(state):
+            self.build(state)
+            self._build_step = state.timestep
             return True
         return False
+
+    def steps_until_check(self, state):
+        """Time steps from now during which no displacement check is due (0 = check now)."""
+        since = state.timestep - getattr(self, "_build_step", state.timestep - 10 ** 9)
+        return max(0, self.rebuild_check_delay - since)
 
     def build(self, state):
         raise NotImplementedError
@@ -148,7 +163,13 @@ class Cell(NeighborList):
             cell_of = torch.empty(n_total, dtype=torch.int32, device=dev)
             cell_start = torch.empty(ncells + 1, dtype=torch.int32, device=dev)
             cell_order = torch.empty(n_total, dtype=torch.int32, device=dev)
-            n_neigh = torch.empty(n_rows, dtype=torch.int32, device=dev)
+            # persistent buffers where the shape allows: consumers that recorded device
+            # addresses (a CUDA graph of the MD step) stay valid across rebuilds
+            if (self.n_neigh is not None and not self._external and self.n_neigh.numel() == n_rows
+                    and self.n_neigh.device == dev):
+                n_neigh = self.n_neigh
+            else:
+                n_neigh = torch.empty(n_rows, dtype=torch.int32, device=dev)
             a.row_offset = lo
             a.n_rows = n_rows
             a.d_cell_of = cell_of.data_ptr()

@@ -98,3 +98,45 @@ def test_nve_conserves_energy_and_momentum():
     assert abs(e1 - e0) < 2e-4 * abs(ig.kinetic_energy()), (e0, e1, ig.kinetic_energy())
     assert np.abs(ig.momentum() - p0).max() < 1e-8 * N
     assert state.timestep == 500
+
+
+def _lj_system(dtype, delay):
+    import azplugins_b200 as az
+    from azplugins_b200 import synth
+
+    rng = np.random.default_rng(12)
+    N = 6000
+    xyz, L = synth.jittered_lattice(N, 0.8, rng, jitter=0.05)
+    v = rng.standard_normal((N, 3))
+    v -= v.mean(axis=0)
+    state = az.State(az.Box.cube(L), ["A"], xyz, velocity=v, dtype=dtype)
+    nl = az.nlist.Cell(buffer=0.4, rebuild_check_delay=delay)
+    plj = az.pair.PerturbedLennardJones(nlist=nl, default_r_cut=3.0, mode="shift")
+    plj.params[("A", "A")] = dict(epsilon=1.0, sigma=1.0, attraction_scale_factor=0.5)
+    bar = az.external.SphericalHarmonicBarrier(location=0.45 * L)
+    bar.params["A"] = dict(k=10.0, offset=0.0)
+    return state, nl, az.md.Integrator(dt=0.002, forces=[plj, bar]).attach(state)
+
+
+def test_graph_replay_equals_eager_steps():
+    """CUDA-graph replay of the un-checked steps (rebuild_check_delay) gives the same trajectory,
+    bit for bit, as launching every step, with the same neighbour-list rebuilds."""
+    runs = {}
+    for graph in (False, True):
+        state, nl, ig = _lj_system(np.float32, delay=6)
+        ig.run(150, graph=graph)
+        torch.cuda.synchronize()
+        runs[graph] = (state.pos.clone(), state.vel.clone(), nl.num_builds, state.timestep)
+    assert runs[False][2] == runs[True][2] and runs[True][2] >= 3
+    assert runs[False][3] == runs[True][3] == 150
+    assert torch.equal(runs[False][0], runs[True][0])
+    assert torch.equal(runs[False][1], runs[True][1])
+
+
+def test_graph_mode_rejects_time_dependent_forces():
+    import azplugins_b200 as az
+
+    state, nl, ig = _lj_system(np.float32, delay=4)
+    ig.forces[1].location = lambda t: 5.0  # a variant: may depend on the time step
+    with pytest.raises(ValueError):
+        ig.run(3, graph=True)
