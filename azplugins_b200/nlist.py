@@ -90,6 +90,8 @@ class NeighborList:
 
     def steps_until_check(self, state):
         """Time steps from now during which no displacement check is due (0 = check now)."""
+        if self.rebuild_check_delay <= 1:
+            return 0  # the default: every compute() checks (also repeated calls at one time step)
         since = state.timestep - getattr(self, "_build_step", state.timestep - 10 ** 9)
         return max(0, self.rebuild_check_delay - since)
 
