@@ -113,19 +113,31 @@ template<class S> class DPDPairEvaluatorGeneralWeight : public PairEvaluatorBase
 
     AZP_D void evalThermoPair(S& force_divr, S& force_divr_cons, S& pair_eng, bool)
         {
+        S r, rinv, base;
+        if (c.half_s < S(1.0))
             {
-            const S rinv = fast::rsqrt(this->rsq);
-            const S r = this->rsq * rinv;
-            const S alpha = dpd_uniform_pm1<S>(m_seed, m_i, m_j, m_timestep);
-            const S fc = c.A * (rinv - c.rcut_inv);
-            force_divr_cons = fc;
-            const S base = fmax(S(1.0) - r * c.rcut_inv, S(0));
-            const S wR = fast::pow(base, c.half_s) * rinv;
-            S f = fc - c.gamma * wR * wR * m_dot;
-            f += c.noise * wR * alpha;
-            force_divr = f;
-            pair_eng = c.A * (c.rcut - r) - S(0.5) * c.A * c.rcut_inv * (this->rcutsq - this->rsq);
+            // s < 2: the weight (1 - r/r_cut)^(s/2) has an infinite slope at the cutoff -- a pair
+            // one ulp of r below r_cut gets (6e-8)^(1/4) = 0.016, not ~0 -- so r and the base are
+            // rounded exactly where the reference's host code rounds them (:203-204, :242):
+            // rinv = 1 / sqrt(rsq), r = 1 / rinv, 1 - r * rcutinv without an FMA. The branch is
+            // uniform per type pair.
+            ref::r_and_rinv(this->rsq, r, rinv);
+            base = fmax(ref::sub(S(1.0), ref::mul(r, c.rcut_inv)), S(0));
             }
+        else
+            {
+            rinv = fast::rsqrt(this->rsq);
+            r = this->rsq * rinv;
+            base = fmax(S(1.0) - r * c.rcut_inv, S(0));
+            }
+        const S alpha = dpd_uniform_pm1<S>(m_seed, m_i, m_j, m_timestep);
+        const S fc = c.A * (rinv - c.rcut_inv);
+        force_divr_cons = fc;
+        const S wR = fast::pow(base, c.half_s) * rinv;
+        S f = fc - c.gamma * wR * wR * m_dot;
+        f += c.noise * wR * alpha;
+        force_divr = f;
+        pair_eng = c.A * (c.rcut - r) - S(0.5) * c.A * c.rcut_inv * (this->rcutsq - this->rsq);
         }
 
     static const char* getName()

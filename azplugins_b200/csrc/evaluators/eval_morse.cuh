@@ -4,9 +4,13 @@
 // implementsEnergyShift).
 //
 // The patch director n = rotate(q, (1,0,0)) is written out for the unit x axis:
-//   n = (s^2 + x^2 - y^2 - z^2, 2 (x y + s z), 2 (x z - s y))      q = (s, x, y, z)
+//   n = (s^2 - |v|^2 + 2 x^2, 2 (s z + x y), 2 (x z - s y))        q = (s, x, y, z)
 // n_i depends only on the row, so the kernel's compiler hoists it out of the neighbour loop.
 // U_Morse(r_cut) for the energy shift is hoisted per type pair.
+//
+// Rounding: the potential is stiff (M_r = 0.03, omega = 20), so the fp32 build rounds r, rhat, n,
+// gamma and Omega exactly where the reference's host code rounds them (see evaluatePair); the
+// products after Omega are not amplified and use contracted FMAs.
 #ifndef AZP_EVAL_MORSE_CUH_
 #define AZP_EVAL_MORSE_CUH_
 
@@ -23,12 +27,17 @@ struct AnisoShapeParametersEmpty
 
 template<class S> AZP_D Vec3<S> patch_director(const Vec4<S>& q)
     {
-    // Scalar4 (x,y,z,w) carries the quaternion (s, v.x, v.y, v.z)
+    // Scalar4 (x,y,z,w) carries the quaternion (s, v.x, v.y, v.z). HOOMD's
+    // rotate(q, b) = (s^2 - |v|^2) b + 2 s (v x b) + 2 (v . b) v for b = (1, 0, 0), rounding
+    // where the library routine rounds (the terms multiplied by the zeros of b drop out exactly)
     const S s = q.x, a = q.y, b = q.z, c = q.w;
+    const S c0 = ref::sub(ref::mul(s, s), ref::dot3(a, b, c, a, b, c));
+    const S c1 = S(2) * s;
+    const S c2 = S(2) * a;
     Vec3<S> n;
-    n.x = (s * s - (a * a + b * b + c * c)) + S(2) * a * a;
-    n.y = S(2) * (s * c) + S(2) * a * b;
-    n.z = S(2) * a * c - S(2) * (s * b);
+    n.x = ref::add(c0, ref::mul(c2, a));
+    n.y = ref::add(ref::mul(c1, c), ref::mul(c2, b));
+    n.z = ref::add(ref::mul(c1, -b), ref::mul(c2, c));
     return n;
     }
 
@@ -115,7 +124,7 @@ template<class S> class AnisoPairEvaluatorTwoPatchMorse
 
     AZP_D bool evaluate(Vec3<S>& force, S& pair_eng, bool energy_shift, Vec3<S>& torque_i, Vec3<S>& torque_j)
         {
-        const S rsq = dr.x * dr.x + dr.y * dr.y + dr.z * dr.z;
+        const S rsq = ref::dot3(dr.x, dr.y, dr.z, dr.x, dr.y, dr.z);
         if (rsq > rcutsq) // the reference rejects only strictly-greater (:135)
             return false;
         evaluatePair(rsq, force, pair_eng, energy_shift, torque_i, torque_j);
@@ -125,9 +134,16 @@ template<class S> class AnisoPairEvaluatorTwoPatchMorse
     // body of evaluate() for a pair already known to satisfy rsq <= rcutsq
     AZP_D void evaluatePair(S rsq, Vec3<S>& force, S& pair_eng, bool, Vec3<S>& torque_i, Vec3<S>& torque_j)
         {
+        // The well exp(-(r - r_eq) / M_r) (M_r = 0.03: one ulp of r is 3e-6 of U) and the patch
+        // switch Omega(gamma) (omega = 20) amplify the fp32 rounding of r, rhat, n and gamma
+        // beyond the parity budget, so everything up to Omega follows the reference's host
+        // sequence rounding for rounding (azp_core.cuh, namespace ref): rsq = dot(dr, dr),
+        // rinv = 1 / sqrt(rsq), r = 1 / rinv (:137-139), rhat = dr * rinv, gamma = dot(rhat, n),
+        // exp() of the math library, Omega = 1 / (1 + e) as an IEEE division. (The argument
+        // rsq of this function was accumulated with FMAs for the cutoff test.)
         S r, rinv;
-        fast::sqrt_and_rsqrt(rsq, r, rinv);
-        const Vec3<S> u {dr.x * rinv, dr.y * rinv, dr.z * rinv};
+        ref::r_and_rinv(ref::dot3(dr.x, dr.y, dr.z, dr.x, dr.y, dr.z), r, rinv);
+        const Vec3<S> u {ref::mul(dr.x, rinv), ref::mul(dr.y, rinv), ref::mul(dr.z, rinv)};
         const Vec3<S> ni = patch_director(quat_i);
         const Vec3<S> nj = patch_director(quat_j);
 
@@ -135,17 +151,17 @@ template<class S> class AnisoPairEvaluatorTwoPatchMorse
         S dUM = S(0);
         if (r > c.r_eq || c.repulsion)
             {
-            const S me = fast::exp(-(r - c.r_eq) * c.M_rinv);
-            const S om = S(1.0) - me;
-            UM = c.M_d * (om * om - S(1.0));
+            const S me = ref::exp(ref::mul(-ref::sub(r, c.r_eq), c.M_rinv));
+            const S om = ref::sub(S(1.0), me);
+            UM = ref::mul(c.M_d, ref::sub(ref::mul(om, om), S(1.0)));
             dUM = S(2.0) * c.M_d * c.M_rinv * me * om;
             }
-        const S gi = u.x * ni.x + u.y * ni.y + u.z * ni.z;
-        const S gie = fast::exp(-c.omega * (gi * gi - c.alpha));
-        const S Oi = fast::rcp(S(1.0) + gie);
-        const S gj = u.x * nj.x + u.y * nj.y + u.z * nj.z;
-        const S gje = fast::exp(-c.omega * (gj * gj - c.alpha));
-        const S Oj = fast::rcp(S(1.0) + gje);
+        const S gi = ref::dot3(u.x, u.y, u.z, ni.x, ni.y, ni.z);
+        const S gie = ref::exp(ref::mul(-c.omega, ref::sub(ref::mul(gi, gi), c.alpha)));
+        const S Oi = ref::rcp(ref::add(S(1.0), gie));
+        const S gj = ref::dot3(u.x, u.y, u.z, nj.x, nj.y, nj.z);
+        const S gje = ref::exp(ref::mul(-c.omega, ref::sub(ref::mul(gj, gj), c.alpha)));
+        const S Oj = ref::rcp(ref::add(S(1.0), gje));
 
         const S OiOj = Oi * Oj;
         const S dU_dr = dUM * OiOj;

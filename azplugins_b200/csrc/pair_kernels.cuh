@@ -312,6 +312,15 @@ template<class E, class S, int NTM> struct TypeLookup
             return tj ? rcB : rcA;
         return tab.rcutsq(index2d(ntypes, ti, tj));
         }
+    // k * rcutsq with the product hoisted out of the neighbour loop for NTM = 1 / 2
+    AZP_D S rcutsq_scaled(unsigned int tj, S k) const
+        {
+        if (NTM == 1)
+            return rcA * k;
+        if (NTM == 2)
+            return tj ? rcB * k : rcA * k;
+        return tab.rcutsq(index2d(ntypes, ti, tj)) * k;
+        }
     AZP_D Cache cache(unsigned int tj) const
         {
         if (NTM == 1)
@@ -578,7 +587,9 @@ template<class E_, class S_, bool VIRIAL, int NTM_> struct DpdFamily
         g.displacement(a.box, pj, dx, dy, dz);
         const S rsq = fma(dz, dz, fma(dy, dy, dx * dx));
         const unsigned int tj = NTM == 1 ? 0u : scalar_as_uint(pj.w);
-        if (rsq < types.rcutsq(tj))
+        // the scan's rsq is accumulated with FMAs; the decisive test (heavy) uses the
+        // reference's rounding of rsq, so the scan admits a margin of a few ulp
+        if (rsq < types.rcutsq_scaled(tj, S(1.0) + S(8) * (sizeof(S) == 4 ? S(1.1920929e-7) : S(2.220446049250313e-16))))
             queue.push(j);
         }
 
@@ -591,10 +602,17 @@ template<class E_, class S_, bool VIRIAL, int NTM_> struct DpdFamily
             const Vec4<S> pj = load4(a.pos, j);
             S dx, dy, dz;
             g.displacement(a.box, pj, dx, dy, dz);
-            const S rsq = fma(dz, dz, fma(dy, dy, dx * dx));
+            // rsq = dot(dx, dx) rounded like the reference's host loop (no FMA): for s < 2 the
+            // weight is not continuous in the last ulp below the cutoff (eval_dpd.cuh), so
+            // both the cutoff decision and r must see the reference's rsq
+            const S rsq = ref::dot3(dx, dy, dz, dx, dy, dz);
             const unsigned int tj = NTM == 1 ? 0u : scalar_as_uint(pj.w);
-            const Cache c = types.cache(tj);
-            accept(a, c, j, rsq, types.rcutsq(tj), dx, dy, dz);
+            const S rcutsq = types.rcutsq(tj);
+            if (rsq < rcutsq)
+                {
+                const Cache c = types.cache(tj);
+                accept(a, c, j, rsq, rcutsq, dx, dy, dz);
+                }
             }
         }
 

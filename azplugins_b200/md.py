@@ -37,6 +37,10 @@ class Integrator:
         if not 1 <= len(self.forces) <= _lib.MD_MAX_FORCES:
             raise ValueError("need 1..%d forces" % _lib.MD_MAX_FORCES)
         self._state = state
+        # HOOMD's integrator pushes its dt into every force (ForceCompute::setDeltaT): the DPD
+        # thermostat scales its random force with rsqrt(dt / (6 gamma kT)), so a State left at
+        # another dt would silently break fluctuation-dissipation
+        state.dt = self.dt
         n = state.N
         self.accel = torch.zeros((n, 4), dtype=state.torch_dtype, device=state.device)
         self.net_force = torch.zeros((n, 4), dtype=state.torch_dtype, device=state.device)
@@ -154,10 +158,10 @@ class Integrator:
     def _capture(self, args, compute_virial, lists):
         """Record one step (no displacement check: the caller replays it only while none is due)."""
         st = self._state
-        saved = [(nl, nl.check_dist) for nl in lists]
+        saved = [(nl, nl._frozen) for nl in lists]
         ts = st.timestep
         for nl, _ in saved:
-            nl.check_dist = False
+            nl.freeze()
         try:
             with torch.cuda.device(st.device):
                 torch.cuda.synchronize()
@@ -167,7 +171,7 @@ class Integrator:
         finally:
             st.timestep = ts  # capturing records the kernels, it does not run them
             for nl, flag in saved:
-                nl.check_dist = flag
+                nl._frozen = flag
         return g
 
     # ---- thermodynamic read-outs (ComputeThermo's quantities) ------------------------------

@@ -36,6 +36,8 @@ class NeighborList:
         self.num_builds = 0
         self._pos_at_build = None
         self._external = False
+        self._frozen = False      # freeze(): benchmarks / graph capture keep the current list
+        self._built_for = None    # (box, r_list matrix) of the last build
 
     # ---- consumers: the list must cover the largest r_cut of every attached potential ------
     def _add_consumer(self, force):
@@ -70,15 +72,38 @@ class NeighborList:
         self._external = True
         return self
 
+    def freeze(self):
+        """Keep the current list whatever the particles do (benchmarks that time the force path
+        alone, CUDA-graph capture of a step, launch tuning). Private to this package's drivers:
+        HOOMD has no such switch -- its ``check_dist=False`` means the opposite (rebuild at every
+        check). Undo with :meth:`thaw`."""
+        self._frozen = True
+        return self
+
+    def thaw(self):
+        self._frozen = False
+        return self
+
+    def _signature(self, state):
+        b = state.box
+        # the consumers bump _tables_version on every params / r_cut / r_on assignment
+        return (tuple(b.L), b.xy, b.xz, b.yz, tuple(bool(p) for p in b.periodic), self.buffer,
+                tuple(getattr(f, "_tables_version", 0) for f in self._consumers))
+
     def compute(self, state):
         """Rebuild when needed (HOOMD ``NeighborList::compute``): never for an adopted list; always
-        when there is none yet; otherwise, once ``rebuild_check_delay`` steps have passed since
-        the last build, when some particle has moved more than half the buffer."""
+        when there is none yet or when the box or an ``r_cut`` changed since the last build;
+        otherwise, once ``rebuild_check_delay`` steps have passed since the last build, when some
+        particle has moved more than half the buffer -- or unconditionally at every check when
+        ``check_dist`` is False (HOOMD's meaning of that flag)."""
         if self._external:
             return False
-        if self.n_neigh is None:
+        if self.n_neigh is not None and self._frozen:
+            return False
+        if self.n_neigh is None or self._built_for != self._signature(state):
             self.build(state)
             self._build_step = state.timestep
+            self._built_for = self._signature(state)
             return True
         if self.steps_until_check(state) > 0:
             return False
@@ -100,7 +125,7 @@ class NeighborList:
 
     def _needs_rebuild(self, state):
         if not self.check_dist or self._pos_at_build is None:
-            return self._pos_at_build is None
+            return True  # check_dist=False: rebuild at every check (HOOMD semantics)
         if self._pos_at_build.shape != state.pos.shape:
             return True
         d = state.pos[:, :3] - self._pos_at_build[:, :3]

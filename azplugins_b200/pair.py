@@ -22,10 +22,15 @@ from .nlist import NeighborList
 class _TypePairDict:
     """``TypeParameterDict(..., len_keys=2)`` work-alike: values keyed by unordered type pairs."""
 
-    def __init__(self, schema=None, default=None):
+    def __init__(self, schema=None, default=None, owner=None):
         self._schema = schema  # ordered {key: python type} or None for scalar entries
         self._default = default
         self._data = {}
+        self._owner = owner  # the potential whose device tables go stale when a value changes
+
+    def _touch(self):
+        if self._owner is not None:
+            self._owner._tables_version += 1
 
     @staticmethod
     def _key(key):
@@ -58,6 +63,7 @@ class _TypePairDict:
                     self[(a, b)] = value
             return
         self._data[self._key(key)] = self._validate(value)
+        self._touch()
 
     def __getitem__(self, key):
         k = self._key(key)
@@ -81,6 +87,7 @@ class _TypePairDict:
     @default.setter
     def default(self, v):
         self._default = self._validate(v)
+        self._touch()
 
 
 class Pair:
@@ -97,9 +104,12 @@ class Pair:
         if not isinstance(nlist, NeighborList):
             raise TypeError("nlist must be an azplugins_b200.nlist.NeighborList")
         self.nlist = nlist
-        self.params = _TypePairDict(schema=dict(self._param_schema))
-        self.r_cut = _TypePairDict(default=None if default_r_cut is None else float(default_r_cut))
-        self.r_on = _TypePairDict(default=float(default_r_on))
+        self._tables_version = 0   # bumped by every params / r_cut / r_on assignment
+        self._uploaded_version = -1
+        self.params = _TypePairDict(schema=dict(self._param_schema), owner=self)
+        self.r_cut = _TypePairDict(default=None if default_r_cut is None else float(default_r_cut),
+                                   owner=self)
+        self.r_on = _TypePairDict(default=float(default_r_on), owner=self)
         self.mode = mode
         self._state = None
         self._launch_shape = (0, 0)  # (block_size, threads_per_particle); 0 = library default
@@ -157,6 +167,19 @@ class Pair:
         if state.device.type != "cuda":
             raise _lib.AzpError("%s runs on CUDA devices only (no CPU fallback)" % type(self).__name__)
         self._state = state
+        self._upload_tables()
+        dev = state.device
+        n = state.N
+        self._force = torch.zeros((n, 4), dtype=state.torch_dtype, device=dev)
+        self._virial = torch.zeros((6, n), dtype=state.torch_dtype, device=dev)
+        self._torque = torch.zeros((n, 4), dtype=state.torch_dtype, device=dev)
+        self._computed_at = None
+        return self
+
+    def _upload_tables(self):
+        """Pack and upload param_type / r_cut^2 / r_on^2 tables (HOOMD re-syncs them whenever a
+        parameter is set; here: at attach and before the next compute after any assignment)."""
+        state = self._state
         bits = 8 * state.dtype.itemsize
         nt = state.ntypes
         psz = kernels.param_size(self._evaluator, bits)
@@ -173,12 +196,7 @@ class Pair:
         self._d_params = torch.from_numpy(table.reshape(-1).copy()).to(dev)
         self._d_rcutsq = torch.from_numpy((rc * rc).T.reshape(-1).copy()).to(dev)
         self._d_ronsq = torch.from_numpy((ro * ro).T.reshape(-1).copy()).to(dev)
-        n = state.N
-        self._force = torch.zeros((n, 4), dtype=state.torch_dtype, device=dev)
-        self._virial = torch.zeros((6, n), dtype=state.torch_dtype, device=dev)
-        self._torque = torch.zeros((n, 4), dtype=state.torch_dtype, device=dev)
-        self._computed = False
-        return self
+        self._uploaded_version = self._tables_version
 
     _attach_hook = attach
 
@@ -203,6 +221,8 @@ class Pair:
         st = self._state
         if st is None:
             raise RuntimeError("potential is not attached to a State")
+        if self._uploaded_version != self._tables_version:
+            self._upload_tables()
         self.nlist.compute(st)
         if self.nlist.storage_mode != "full":
             raise RuntimeError("GPU pair potentials need a full neighbour list")
@@ -241,7 +261,9 @@ class Pair:
             return self
         with torch.cuda.device(self._state.device):
             kernels.launch(self._family, self._evaluator, self._bits, args, self._d_params.data_ptr())
-        self._computed = True
+        if row_ids is None and rows is None:
+            self._computed_at = (self._state.timestep if timestep is None else int(timestep),
+                                 self._tables_version)
         return self
 
     def compute_to_host(self, host_force, host_virial=None, host_torque=None, timestep=None,
@@ -292,7 +314,9 @@ class Pair:
 
     # ---- read-outs (hoomd.md.force.Force) ------------------------------------------------------
     def _need(self):
-        if not getattr(self, "_computed", False):
+        # ForceCompute::compute(timestep) semantics: evaluate once per time step (and again after
+        # a parameter change); an explicit compute() always re-evaluates
+        if getattr(self, "_computed_at", None) != (self._state.timestep, self._tables_version):
             self.compute()
 
     @property

@@ -383,7 +383,8 @@ class SliceScheduler:
             self.halo(self.exchange_arrays)
         torch.cuda.synchronize()
         for pot in self.pots:
-            pot.nlist.check_dist = False
+            was_frozen = pot.nlist._frozen
+            pot.nlist.freeze()
             rows = None
             if self.peer_halo is None and self.plan.interior_rows.numel():
                 rows = self.plan.interior_rows
@@ -394,6 +395,7 @@ class SliceScheduler:
                                         pot._d_params.data_ptr())
             pot.kernel_parameters = (b, t)
             out.append((b, t, ms))
+            pot.nlist._frozen = was_frozen
         return out
 
     def time_kernels(self, steps, compute_virial=False):

@@ -279,7 +279,7 @@ def run_b200(args):
         nl.compute(state)
         # the list is frozen for the run: the per-step displacement check (a device->host flag
         # read) belongs to the neighbour-list row, not to the force path that is timed here
-        nl.check_dist = False
+        nl.freeze()
         torch.cuda.synchronize()
         tuned = []
         for p in pots:

@@ -14,19 +14,25 @@ Error measures (all computed in float64):
                    measure that cancellation instead of the arithmetic;
 Budgets: fp32 1e-5 (force, torque), fp64 1e-10; energy and virial 1e-6 (fp32), 1e-10 (fp64).
 
-Ill-conditioned potentials in fp32. Two evaluators amplify the rounding of r itself beyond those
-budgets in ANY fp32 implementation: the two-patch Morse well (exp(-(r - r_eq)/0.03): 1 ulp of r
-is 3e-6 of U) and the DPD weight (1 - r/r_cut)^(s/2) with s < 2 (infinite slope at the cutoff).
-The reference's own fp32 CPU result is then farther than the budget from its fp64 result. For
-those cases `truth` (the fp64 oracle on the same fp32-rounded inputs) may be given; the check
-passes when the CUDA result is within budget of the fp32 oracle OR is no farther from the fp64
-truth than 2x the fp32 oracle itself is (floored at the budget).
+Criterion. Every check reports, per quantity, WHICH criterion it passed on:
+  "strict"      -- within the BASELINE.json budget of the oracle in the SAME precision;
+  "fp64-escape" -- outside that budget, but no farther from the fp64 oracle (run on the same
+                   fp32-rounded inputs) than 2x the fp32 oracle itself is (floored at the budget).
+The escape is a builder-defined relaxation and is OFF unless a test passes ``truth=`` -- which
+only the cases listed in ``ESCAPE_ALLOWED`` (and named in DESIGN.md section 5) may do. Round 2
+made the two ill-conditioned fp32 potentials (two-patch Morse well, DPD weight with s < 2) round
+their stiff intermediate results exactly where the reference's host code rounds them
+(csrc/azp_core.cuh, namespace ref), so the list is empty: every case must pass "strict".
+``report["criterion"]`` maps quantity -> criterion; smoke() prints it.
 """
 
 import numpy as np
 
 FORCE_TOL = {4: 1e-5, 8: 1e-10}
 TOTAL_TOL = {4: 1e-6, 8: 1e-10}
+
+# (config, potential class) pairs that may pass on the fp64-escape criterion. Empty on purpose.
+ESCAPE_ALLOWED = frozenset()
 
 
 def per_particle_rel_err(a, ref):
@@ -124,6 +130,64 @@ def oracle_compute(orc, state, pot, nl_arrays, virial=True, n_rows=None, half=Fa
     return dict(force=f, torque=None, virial=v)
 
 
+def sample_rows_arrays(state, nl, rows):
+    """A bounded oracle problem for an ARBITRARY set of rows of a large system (full-size parity,
+    tests/test_gpu_fullsize.py). The oracle evaluates rows [0, m) of whatever arrays it is given,
+    so the sample is laid out as a system of m "local" particles (copies of the sampled
+    particles, in sample order) followed by the whole original particle array as "ghosts": the
+    sampled rows' neighbour lists are copied out of the device list and their entries shifted by
+    m. Same particles, same neighbours in the same order -> the same per-row arithmetic.
+    Returns (state-like dict of host arrays, (n_neigh, nlist, head_list), m)."""
+    import torch
+
+    rows_t = torch.as_tensor(np.asarray(rows, dtype=np.int64), device=nl.n_neigh.device)
+    m = int(rows_t.numel())
+    nn = nl.n_neigh[rows_t].to(torch.int64)
+    head = nl.head_list[rows_t]
+    start = torch.cumsum(nn, 0) - nn
+    total = int(nn.sum().item())
+    k = torch.arange(total, device=nn.device) - torch.repeat_interleave(start, nn)
+    src = torch.repeat_interleave(head, nn) + k
+    entries = nl.nlist[src].to(torch.int64) + m
+    arrays = (nn.cpu().numpy().astype(np.uint32), entries.cpu().numpy().astype(np.uint32),
+              start.cpu().numpy().astype(np.uint64))
+
+    def stacked(t):
+        return torch.cat([t[rows_t], t[: state.pos.shape[0]]]).cpu().numpy()
+
+    host = dict(pos=stacked(state.pos), vel=stacked(state.vel), orientation=stacked(state.orientation),
+                tag=stacked(state.tag).view(np.uint32))
+    return host, arrays, m
+
+
+class _HostState:
+    """Just enough of azplugins_b200.State for oracle_compute, over host arrays."""
+
+    def __init__(self, state, host):
+        import torch
+
+        self.types, self.ntypes, self.box = state.types, state.ntypes, state.box
+        self.seed, self.timestep, self.dt = state.seed, state.timestep, state.dt
+        self.pos = torch.from_numpy(host["pos"])
+        self.vel = torch.from_numpy(host["vel"])
+        self.orientation = torch.from_numpy(host["orientation"])
+        self.tag = torch.from_numpy(host["tag"].view(np.int32))
+        self.N = self.pos.shape[0]
+
+
+def oracle_compute_rows(orc, state, pot, nl, rows, virial=True):
+    """Oracle result for the rows ``rows`` of a large system (see sample_rows_arrays): dict with
+    force (m,4), virial (6,m), torque (m,4) or None, in sample order."""
+    host, arrays, m = sample_rows_arrays(state, nl, rows)
+    out = oracle_compute(orc, _HostState(state, host), pot, arrays, virial=virial, n_rows=m)
+    out["force"] = out["force"][:m]
+    if out.get("torque") is not None:
+        out["torque"] = out["torque"][:m]
+    if out.get("virial") is not None:
+        out["virial"] = out["virial"][:, :m]
+    return out
+
+
 def _errors(F, E, W, T, ref, sl, virial):
     out = dict(force=per_particle_rel_err(F, ref["force"][sl, :3]),
                energy=total_rel_err(E, ref["force"][sl, 3]))
@@ -135,15 +199,26 @@ def _errors(F, E, W, T, ref, sl, virial):
 
 
 def check_against_oracle(pot, ref, itemsize, n_rows=None, force_tol=None, total_tol=None,
-                         virial=True, truth=None):
+                         virial=True, truth=None, rows=None):
     """Assert the product's read-outs match an oracle result within the stated budgets
-    (see the module docstring for `truth`). Returns the measured errors."""
+    (see the module docstring for `truth`). ``rows``: the product rows that correspond to the
+    oracle's rows [0, len(rows)) (oracle_compute_rows). Returns the measured errors."""
     ftol = FORCE_TOL[itemsize] if force_tol is None else force_tol
     ttol = TOTAL_TOL[itemsize] if total_tol is None else total_tol
     sl = slice(0, n_rows)
-    F, E = pot.forces[sl], pot.energies[sl]
-    W = pot.virials[sl] if virial else None
-    T = pot.torques[sl] if ref.get("torque") is not None else None
+    if rows is not None:
+        import torch
+
+        rt = torch.as_tensor(np.asarray(rows, dtype=np.int64), device=pot._force.device)
+        fsel = pot._force[rt].cpu().numpy()
+        F, E = fsel[:, :3], fsel[:, 3]
+        W = pot._virial[:, rt].cpu().numpy().T if virial else None
+        T = pot._torque[rt].cpu().numpy()[:, :3] if ref.get("torque") is not None else None
+        sl = slice(0, len(rows))
+    else:
+        F, E = pot.forces[sl], pot.energies[sl]
+        W = pot.virials[sl] if virial else None
+        T = pot.torques[sl] if ref.get("torque") is not None else None
     report = _errors(F, E, W, T, ref, sl, virial)
     budget = dict(force=ftol, torque=ftol, energy=ttol, virial=ttol)
     if truth is not None:
@@ -153,11 +228,22 @@ def check_against_oracle(pot, ref, itemsize, n_rows=None, force_tol=None, total_
                         None if not virial else ref["virial"][:, sl].T, refT, truth, sl, virial)
         report.update({k + "_vs_fp64": v for k, v in gpu_t.items()})
         report.update({k + "_cpu32_vs_fp64": v for k, v in cpu_t.items()})
+    criterion = {}
     for k, b in budget.items():
         if k not in report:
             continue
         ok = report[k] <= b
+        criterion[k] = "strict"
         if not ok and truth is not None:
             ok = report[k + "_vs_fp64"] <= max(b, 2.0 * report[k + "_cpu32_vs_fp64"])
+            criterion[k] = "fp64-escape"
         assert ok, "%s rel err %.3e > %.1e (%s)" % (k, report[k], b, report)
+    report["criterion"] = criterion
     return report
+
+
+def format_report(report):
+    """One line: quantity=error[criterion] ... (what smoke() and the tests print)."""
+    crit = report.get("criterion", {})
+    return " ".join("%s=%.2e[%s]" % (k, report[k], crit[k]) for k in ("force", "torque", "energy", "virial")
+                    if k in crit)

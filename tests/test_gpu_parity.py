@@ -34,7 +34,7 @@ def run_config(cfg, dtype, N=None, virial=True, modes=None, kinds=("best",), tpp
             arrays = nl.to_numpy()
             its = np.dtype(dtype).itemsize
             truth = None
-            if its == 4:
+            if its == 4 and (cfg, type(pot).__name__) in helpers.ESCAPE_ALLOWED:
                 truth = helpers.oracle_compute(oracle.load("best", np.float64), state, pot, arrays,
                                                virial=virial)
             for kind in kinds:
@@ -53,7 +53,8 @@ def run_config(cfg, dtype, N=None, virial=True, modes=None, kinds=("best",), tpp
 def test_config_matches_oracle(cfg, dtype):
     reports, *_ = run_config(cfg, dtype)
     for r in reports:
-        print(r)
+        print(r[:4], helpers.format_report(r[4]))
+        assert set(r[4]["criterion"].values()) == {"strict"}
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64], ids=["f32", "f64"])
@@ -70,11 +71,19 @@ def test_fp32_and_fp64_against_fp64_truth(dtype):
     pot.compute()
     arrays = nl.to_numpy()
     # same (dtype-rounded) inputs, fp64 arithmetic. For fp32 the distance to the fp64 result is
-    # set by fp32 rounding of ~124 partially cancelling terms per particle; the criterion is the
-    # budget or, failing that, "no farther from fp64 than 2x the fp32 CPU reference is".
+    # set by fp32 rounding of ~124 partially cancelling terms per particle, which no fp32
+    # implementation escapes: the CUDA result must be no farther from fp64 than 2x the fp32 CPU
+    # reference is (floored at the budget) -- and, separately, within the strict budget of the
+    # fp32 oracle.
     truth = helpers.oracle_compute(oracle.load("best", np.float64), state, pot, arrays)
     ref = helpers.oracle_compute(oracle.load("best", dtype), state, pot, arrays)
-    rep = helpers.check_against_oracle(pot, ref, np.dtype(dtype).itemsize, truth=truth)
+    its = np.dtype(dtype).itemsize
+    rep = helpers.check_against_oracle(pot, ref, its)
+    assert set(rep["criterion"].values()) == {"strict"}
+    rep = helpers.check_against_oracle(pot, ref, its, truth=truth)
+    for k in rep["criterion"]:
+        budget = helpers.FORCE_TOL[its] if k in ("force", "torque") else helpers.TOTAL_TOL[its]
+        assert rep[k + "_vs_fp64"] <= max(budget, 2.0 * rep[k + "_cpu32_vs_fp64"]), (k, rep)
     print("vs fp64 truth", np.dtype(dtype).name, rep)
 
 
@@ -143,12 +152,10 @@ def test_dpd_random_stream_matches_oracle():
             (pot,) = wl.make_potentials(nl)
             pot.attach(state).compute()
             ref = helpers.oracle_compute(oracle.load("best", dtype), state, pot, nl.to_numpy())
-            truth = None
-            if dtype == np.float32:
-                truth = helpers.oracle_compute(oracle.load("best", np.float64), state, pot,
-                                               nl.to_numpy())
-            print("dpd stream", dtype.__name__, s,
-                  helpers.check_against_oracle(pot, ref, np.dtype(dtype).itemsize, truth=truth))
+            # strict budget also for s = 0.5 (the weight has an infinite slope at the cutoff;
+            # the kernel rounds r and 1 - r/r_cut where the reference's host code does)
+            rep = helpers.check_against_oracle(pot, ref, np.dtype(dtype).itemsize)
+            print("dpd stream", dtype.__name__, s, helpers.format_report(rep))
             # and the stream really depends on seed and timestep
             f0 = pot.forces.copy()
             state.seed = 43

@@ -140,3 +140,41 @@ def test_graph_mode_rejects_time_dependent_forces():
     ig.forces[1].location = lambda t: 5.0  # a variant: may depend on the time step
     with pytest.raises(ValueError):
         ig.run(3, graph=True)
+
+
+def test_dpd_temperature_reference_test():
+    """The reference's only test of the DPD thermostat, src/pytest/test_pair_dpd.py:13-46,
+    reproduced step for step: 10^3 simple-cubic lattice (a = 0.6, box 6 x 6 x 6), momenta
+    thermalised at kT = 1.5, DPDGeneralWeight(kT = 1.5, r_cut = 1) with A = 0, gamma = 4.5,
+    s = 0.5 (random + drag part only), Cell(buffer = 0.4), NVE at dt = 0.01; 10 steps, then the
+    kinetic temperature averaged over 100 steps must be 1.5 within 10 %. This is the one
+    reference-held check of the random force (amplitude, weight, Philox stream statistics)."""
+    import azplugins_b200 as az
+
+    n, a, kT = 10, 0.6, 1.5
+    g = (np.arange(n) + 0.5) * a - 0.5 * n * a
+    xyz = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)
+    rng = np.random.default_rng(12)
+    vel = rng.standard_normal(xyz.shape) * np.sqrt(kT)
+    vel -= vel.mean(axis=0)  # thermalize_particle_momenta removes the centre-of-mass momentum
+    N = len(xyz)
+    ndof = 3 * N - 3
+    vel *= np.sqrt(kT * ndof / (vel ** 2).sum())  # ... and rescales to kT exactly
+    for dtype in (np.float32, np.float64):
+        # the State is created at another dt on purpose: the integrator's dt must reach the force
+        state = az.State(az.Box.cube(n * a), ["A"], xyz, velocity=vel, dtype=dtype, seed=7, dt=0.005)
+        cell = az.nlist.Cell(buffer=0.4)
+        dpd = az.pair.DPDGeneralWeight(nlist=cell, kT=kT, default_r_cut=1.0)
+        dpd.params[("A", "A")] = dict(A=0.0, gamma=4.5, s=0.5)
+        ig = az.md.Integrator(dt=0.01, forces=[dpd], methods=[az.md.ConstantVolume()]).attach(state)
+        assert state.dt == 0.01
+        ig.run(10)
+        samples = np.zeros(100)
+        for k in range(100):
+            samples[k] = 2.0 * ig.kinetic_energy() / ndof
+            ig.run(1)
+        avg = samples.mean()
+        print("DPD thermostat <kT> =", avg, np.dtype(dtype).name)
+        assert avg == pytest.approx(1.5, 0.1)
+        # momentum is conserved by the pairwise random and drag forces
+        assert np.abs(ig.momentum()).max() < 1e-2 * np.sqrt(N * kT)

@@ -26,7 +26,7 @@ for dtype in (np.float32, np.float64):
         nl.build(state)
     torch.cuda.synchronize()
     t_build = (time.perf_counter() - t0) / 5
-    nl.check_dist = False
+    nl.freeze()
     b, t, ms = pot.tune_kernel_parameters(compute_virial=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for _ in range(3):
