@@ -15,7 +15,10 @@ CPU baseline, end-to-end number and clocks (contract: task statement section 4).
   positions from pinned host memory to the device and the forces (+virial) back;
 * `roofline`: algorithmic bytes (SURVEY.md 8(d)) / measured kernel time vs MEASURED_PEAKS.json;
 * `cpu_baseline` / `--impl reference`: the CPU oracle (oracle/_ref = the reference's own evaluator
-  headers under the restated HOOMD loop, else the port) on the host cores, bounded row sample.
+  headers under the restated HOOMD loop, else the port) on the host cores, bounded row sample;
+  the reference arm never imports the product package (no libazp_b200.so in its process);
+* `check` (N > 1): rows of every rank's slice against a single-domain evaluation;
+* `strong_scaling`: BASELINE.json's scaling case, C5 TwoPatchMorse N = 16 M in total, at this N.
 """
 
 import argparse
@@ -45,12 +48,30 @@ def emit(line):
 
 METRIC = "pair_force_particle_steps_per_s"
 UNIT = "particle-steps/s"
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the
-# committed `ncu --set full` capture of this command (profiles/); None until captured.
-NCU_TRAFFIC_BYTES = {"C2": 614.97e6}  # profiles/r01_c2_ncu_full_v7_summary.csv (578.60 + 36.37 MB)
-# warp instructions executed per launch of the same capture (smsp__inst_executed.sum): the kernel
-# is instruction-issue bound, not HBM bound, so the issue floor is reported beside the HBM roofline
-NCU_WARP_INSTRUCTIONS = {"C2": 217.95e6}
+
+
+def ncu_constants(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum and smsp__inst_executed.sum per launch of the
+    dominant kernel, from the committed `ncu --set full` capture of this workload
+    (profiles/ncu_constants.json, written by tools/ncu_summary.py --register). A capture taken
+    with other kernel sources than the ones this run was built from is NOT reported: the entry
+    carries the source hash at capture time (tools/srchash.py) and must match."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from srchash import kernel_source_hash
+
+    path = os.path.join(ROOT, "profiles", "ncu_constants.json")
+    here = kernel_source_hash()
+    if not os.path.exists(path):
+        return None, "no capture registered", here
+    entry = json.load(open(path)).get(workload)
+    if entry is None:
+        return None, "no capture registered for %s" % workload, here
+    if entry.get("kernel_sources") != here:
+        return None, ("stale capture %s (kernel sources %s, this build %s)"
+                      % (entry.get("summary"), entry.get("kernel_sources"), here)), here
+    return entry, entry.get("summary"), here
+
+
 SM_COUNT, SCHEDULERS_PER_SM = 148, 4
 
 
@@ -65,6 +86,10 @@ def parse():
     ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
                     help="multi-GPU halo transport: NVLink peer-memory push (default) or NCCL send/recv")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the e2e leg")
+    ap.add_argument("--no-strong", action="store_true",
+                    help="skip the C5 N = 16 M strong-scaling record appended to the C2 line")
+    ap.add_argument("--strong-n", type=int, default=16000000)
     ap.add_argument("--no-tune", action="store_true")
     ap.add_argument("--block", type=int, default=0, help="pin block_size (with --no-tune)")
     ap.add_argument("--tpp", type=int, default=0, help="pin threads_per_particle (with --no-tune)")
@@ -141,25 +166,48 @@ def timed_with_clocks(fn, device_index, probe=None):
 # -------------------------------------------------------------------------------------------------
 # CPU side: the oracle on the host cores (cpu_baseline of the b200 arm; the whole reference arm)
 # -------------------------------------------------------------------------------------------------
-def cpu_oracle_rate(wl, target_seconds=8.0, steps=1, warmup=0, quiet=True):
-    """particle-steps/s of the oracle loop on a bounded sample of rows of `wl` (fp32, full list,
-    all host threads). Returns (value, info dict)."""
+def load_synth_without_product_library():
+    """The workload generator (numpy only) for the CPU arm WITHOUT importing the product package:
+    `import azplugins_b200` dlopens libazp_b200.so, and a reference arm that maps the product
+    library is exactly what the driver's loaded-library record exists to catch. The generator's
+    modules (synth, box, state) are loaded under a private package name whose __init__ is
+    empty, so azplugins_b200/__init__.py never runs."""
+    import importlib
+    import types
+
+    name = "_azp_workloads_only"
+    if name not in sys.modules:
+        pkg = types.ModuleType(name)
+        pkg.__path__ = [os.path.join(ROOT, "azplugins_b200")]
+        sys.modules[name] = pkg
+    synth = importlib.import_module(name + ".synth")
+    state = importlib.import_module(name + ".state")
+    assert "azplugins_b200" not in sys.modules or True
+    return synth, state.pack_pos
+
+
+def cpu_oracle_rate(wl, pack_pos, target_seconds=8.0, steps=1, warmup=0):
+    """particle-steps/s of the reference's CPU path on the host cores: the oracle loop
+    (oracle/_ref = the reference's own evaluator headers under the restated HOOMD host loop, else
+    the port) on a bounded sample of rows of `wl`, fp32, every host thread.
+
+    Two parallel modes are timed and the faster one is the value (both are reported):
+      "domains"   -- HOOMD's CPU parallelism: one half-list domain per thread (MPI domain
+                     decomposition restated with OpenMP, oracle/driver_loops.h): a pair inside a
+                     domain is evaluated once, a pair across a domain face on both sides;
+      "full-list" -- every row evaluates its whole full-list row (what the GPU kernel does).
+    plus one thread with a true half list (what a single HOOMD CPU rank does)."""
     from oracle import oracle
 
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
     orc = oracle.load("best", np.float32)
     kind = "reference" if orc.kind == "ref" else "port"
     cores = orc.max_threads()
-    from azplugins_b200.state import pack_pos
-
     pos = pack_pos(wl.position, wl.typeid, np.float32)
     spec = wl.potentials
     nt = len(wl.types)
 
     def tables(s):
-        name = {"PerturbedLennardJones": "PerturbedLennardJones", "ExpandedYukawa": "ExpandedYukawa",
-                "DPDGeneralWeight": "DPDGeneralWeight", "TwoPatchMorse": "TwoPatchMorse",
-                "Colloid": "Colloid", "Hertz": "Hertz"}[s["cls"]]
+        name = s["cls"]
         rc = np.full((nt, nt), float(s["default_r_cut"]))
         pp = {}
         for (a, b), p in s["params"].items():
@@ -171,53 +219,58 @@ def cpu_oracle_rate(wl, target_seconds=8.0, steps=1, warmup=0, quiet=True):
 
     tabs = [tables(s) for s in spec]
     rc_max = np.max([t[2] for t in tabs], axis=0)
-
+    r_list = np.where(rc_max > 0, rc_max + 0.4, 0.0)
+    vel = None
+    if wl.velocity is not None:
+        vel = np.zeros((len(pos), 4), dtype=np.float32)
+        vel[:, :3] = wl.velocity
+    quat = None if wl.orientation is None else wl.orientation.astype(np.float32)
     lists = {}
 
-    def run(n_rows, nthreads=0):
-        if n_rows not in lists:
+    def run(n_rows, half=False, nthreads=0):
+        key = (n_rows, half is True)
+        if key not in lists:
             lists.clear()
-            lists[n_rows] = orc.build_nlist(pos, wl.box.L, rc_max + 0.4, ntypes=nt, n_rows=n_rows)
-        nn, nl, head = lists[n_rows]
+            lists[key] = orc.build_nlist(pos, wl.box.L, r_list, ntypes=nt, n_rows=n_rows,
+                                         half=half is True)
+        nn, nl, head = lists[key]
+        common = dict(ntypes=nt, virial=wl.compute_virial, N=n_rows, nthreads=nthreads, half=half)
         t0 = time.perf_counter()
         for s, (name, table, rc) in zip(spec, tabs):
             mode = s.get("kwargs", {}).get("mode", "none")
             if name == "TwoPatchMorse":
-                orc.aniso_forces(table, pos, wl.orientation.astype(np.float32), nn, nl, head,
-                                 wl.box.L, rc, ntypes=nt, mode=mode, virial=wl.compute_virial,
-                                 N=n_rows, nthreads=nthreads)
+                orc.aniso_forces(table, pos, quat, nn, nl, head, wl.box.L, rc, mode=mode, **common)
             elif name == "DPDGeneralWeight":
-                vel = np.zeros((len(pos), 4), dtype=np.float32)
-                vel[:, :3] = wl.velocity
                 orc.dpd_forces(table, pos, vel, wl.tag, nn, nl, head, wl.box.L, rc, wl.seed,
-                               wl.timestep, wl.dt, s["kwargs"]["kT"], ntypes=nt,
-                               virial=wl.compute_virial, N=n_rows, nthreads=nthreads)
+                               wl.timestep, wl.dt, s["kwargs"]["kT"], **common)
             else:
-                orc.pair_forces(name, table, pos, nn, nl, head, wl.box.L, rc, ntypes=nt,
-                                mode=mode, virial=wl.compute_virial, N=n_rows, nthreads=nthreads)
+                orc.pair_forces(name, table, pos, nn, nl, head, wl.box.L, rc, mode=mode, **common)
         return time.perf_counter() - t0
 
     probe_rows = min(wl.N, 20000)
-    t_probe = run(probe_rows)
-    n_rows = int(min(wl.N, max(probe_rows, probe_rows * target_seconds / max(t_probe, 1e-6))))
-    for _ in range(warmup):
-        run(n_rows)
-    times = [run(n_rows) for _ in range(max(1, steps))]
-    t = float(np.median(times))
-    # one thread on the same rows (what a single HOOMD CPU rank does); the list
-    # of the sample is reused, the pass is bounded by taking the probe's rows
-    t1 = run(n_rows, nthreads=1) if n_rows <= 4 * probe_rows else None
-    if t1 is None:
-        lists.clear()
-        t1_rows = probe_rows
-        t1 = run(t1_rows, nthreads=1)
-    else:
-        t1_rows = n_rows
-    info = {"value": n_rows / t, "unit": UNIT, "cores": cores, "kind": kind,
-            "value_1_thread": t1_rows / t1,
-            "sample": "first %d of %d rows of %s, full neighbour list, fp32, %.2f s per pass "
-                      "(HOOMD's CPU classes would use a half list: half the pair evaluations)"
-                      % (n_rows, wl.N, wl.name, t)}
+    t_probe = min(run(probe_rows), run(probe_rows))
+    # one pass over the sample should take ~target_seconds / (passes below); the whole system
+    # when it fits
+    per_pass = target_seconds / (2.0 * (max(1, steps) + warmup) + 1.0)
+    n_rows = int(min(wl.N, max(probe_rows, probe_rows * per_pass / max(t_probe, 1e-6))))
+    out = {}
+    for mode, half in (("full-list", False), ("domains", "domains")):
+        for _ in range(warmup):
+            run(n_rows, half)
+        out[mode] = float(np.median([run(n_rows, half) for _ in range(max(1, steps))]))
+    best = min(out, key=out.get)
+    t = out[best]
+    # one thread, true half list (third law), on the probe's rows
+    t1 = run(probe_rows, half=True, nthreads=1)
+    info = {"value": n_rows / t, "unit": UNIT, "cores": cores, "kind": kind, "mode": best,
+            "value_domains_half_list": n_rows / out["domains"],
+            "value_full_list": n_rows / out["full-list"],
+            "value_1_thread_half_list": probe_rows / t1,
+            "build": "g++ -O3 -march=x86-64-v3 -ffp-contract=off (oracle/Makefile)",
+            "sample": "%s %d of %d rows of %s, fp32, %.3f s per pass, %d threads; the faster of "
+                      "one half-list domain per thread (HOOMD's MPI decomposition) and the "
+                      "full-list loop"
+                      % ("all" if n_rows == wl.N else "first", n_rows, wl.N, wl.name, t, cores)}
     return n_rows / t, info, t
 
 
@@ -225,16 +278,18 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from azplugins_b200 import synth  # numpy-only generator
-
+    synth, pack_pos = load_synth_without_product_library()
     n = args.n_per_gpu or DEFAULT_N[args.workload]
     wl = synth.CONFIGS[args.workload](N=n * max(1, args.gpus) if args.gpus > 1 else n)
-    value, info, t = cpu_oracle_rate(wl, target_seconds=4.0, steps=args.steps, warmup=args.warmup)
+    budget = 60.0  # seconds of CPU work for the whole --steps/--warmup run
+    value, info, t = cpu_oracle_rate(wl, pack_pos, target_seconds=budget, steps=args.steps,
+                                     warmup=args.warmup)
+    assert "azplugins_b200" not in sys.modules, "the reference arm must not load the product"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl.name, "N": wl.N, "note": "CPU oracle on host cores"},
+            "config": config_of(wl, args.gpus),
             "cpu_baseline": info,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},
@@ -242,14 +297,132 @@ def run_reference(args):
     emit(line)
 
 
+def config_of(wl, n_gpus):
+    """The workload description shared by both arms (same keys, same values)."""
+    return {"workload": wl.name, "N": int(wl.N), "particles_per_gpu": int(wl.N // max(1, n_gpus)),
+            "types": len(wl.types), "compute_virial": bool(wl.compute_virial),
+            "potentials": [s["cls"] for s in wl.potentials], "r_buff": 0.4, "precision": "fp32"}
+
+
 # -------------------------------------------------------------------------------------------------
 # B200 arm
 # -------------------------------------------------------------------------------------------------
+class Job:
+    """One workload set up on this rank's GPU (single GPU) or as this rank's particle slice."""
+
+    def __init__(self, wl, args, torch, dist, dev, rank, world):
+        import azplugins_b200 as az
+        from azplugins_b200 import synth
+
+        self.wl, self.args, self.torch, self.dist = wl, args, torch, dist
+        self.dev, self.rank, self.world, self.multi = dev, rank, world, world > 1
+        self.virial = wl.compute_virial
+        if not self.multi:
+            self.state = wl.make_state(dtype=np.float32, device=dev)
+            self.nl = az.nlist.Cell(buffer=synth.BUFFER)
+            self.pots = wl.make_potentials(self.nl)
+            for p in self.pots:
+                p.attach(self.state)
+            self.nl.compute(self.state)
+            # the list is frozen for the run: the per-step displacement check belongs to the
+            # neighbour-list row, not to the force path that is timed here
+            self.nl.freeze()
+            torch.cuda.synchronize()
+            self.tuned = []
+            for p in self.pots:
+                if not args.no_tune:
+                    self.tuned.append(p.tune_kernel_parameters(compute_virial=self.virial))
+                else:
+                    p.kernel_parameters = (args.block, args.tpp)
+                    self.tuned.append(p.kernel_parameters + (None,))
+            self.sched = None
+            self.launches_per_step = len(self.pots) + sum(1 for _ in self.pots if self.nl.n_max > 512)
+            self.n_local = wl.N
+            self.n_bar = float(self.nl.n_neigh[:self.state.N].double().mean().item())
+            self.exchange_bytes = 0
+        else:
+            from azplugins_b200 import slices
+
+            self.sched = slices.SliceScheduler.from_workload(
+                wl, rank, world, dev, dtype=np.float32, buffer=synth.BUFFER, transport=args.transport)
+            self.tuned = [] if args.no_tune else self.sched.tune(compute_virial=self.virial)
+            self.pots = self.sched.pots
+            self.launches_per_step = self.sched.launches_per_step
+            self.n_local = self.sched.n_local
+            self.n_bar = self.sched.mean_row_length()
+            self.exchange_bytes = self.sched.exchange_bytes_per_step()
+
+    def step(self):
+        if self.sched is not None:
+            self.sched.step(compute_virial=self.virial)
+        else:
+            for p in self.pots:
+                p.compute(compute_virial=self.virial)
+
+    def barrier(self):
+        if self.multi:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, *vals):
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device=self.dev)
+        if self.multi:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t.tolist()]
+
+    def time_steps(self, K):
+        """ms for K steps between two events on the launching stream, barrier + synchronize on
+        both sides, max over ranks."""
+        torch = self.torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        e0.record()
+        for _ in range(K):
+            self.step()
+        e1.record()
+        self.barrier()
+        return self.max_over_ranks(e0.elapsed_time(e1))[0]
+
+    def kernel_ms(self, K):
+        """ms per step of the force kernels alone (at N = 1 the step is kernel-only)."""
+        if self.sched is None:
+            return None
+        return self.max_over_ranks(self.sched.time_kernels(K, compute_virial=self.virial))[0]
+
+    def roofline(self, kern_ms, hbm_peak, peak_src):
+        wl = self.wl
+        # per potential: fixed arrays + the neighbour list once (SURVEY.md 8(d)); a workload with
+        # two potentials (C3) streams the list twice, and the step time covers both launches
+        n_pot = len(wl.potentials)
+        bytes_fixed = wl.bytes_per_particle - 4.0 * wl.n_bar if wl.bytes_per_particle else 44.0
+        alg_bytes = (bytes_fixed + 4.0 * self.n_bar) * self.n_local * n_pot
+        achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+        return {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "frac_of_nominal_8TBs": achieved / 8000.0, "kernel_ms": kern_ms,
+                "algorithmic_bytes_per_step": alg_bytes,
+                "bytes_per_particle": (bytes_fixed + 4.0 * self.n_bar) * n_pot,
+                "mean_row_length": self.n_bar, "launches_per_step": self.launches_per_step}
+
+    def check(self):
+        """Multi-GPU: rows of this rank's slice against a single-domain evaluation on this GPU
+        (slices.SliceScheduler.verify_against_single_domain); worst case over ranks."""
+        if self.sched is None:
+            return None
+        c = self.sched.verify_against_single_domain(self.wl, compute_virial=self.virial)
+        worst, not_identical = self.max_over_ranks(c["max_rel_diff"], 0.0 if c["bit_identical"] else 1.0)
+        return {"what": "first %d + middle %d rows of every rank's slice vs a single-domain "
+                        "evaluation of the whole system on the same GPU, after the timed steps"
+                        % (4096, 4096),
+                "rows_per_rank": c["rows"], "max_rel_diff_over_ranks": worst,
+                "bit_identical_on_every_rank": not_identical == 0.0,
+                "ok": worst <= 1e-5}
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
 
-    import azplugins_b200 as az
     from azplugins_b200 import synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -269,71 +442,13 @@ def run_b200(args):
     n_total = wl.N
     K, W = args.steps, max(3, args.warmup)
     hbm_peak, peak_src = peaks()
-
-    if not multi:
-        state = wl.make_state(dtype=np.float32, device=dev)
-        nl = az.nlist.Cell(buffer=synth.BUFFER)
-        pots = wl.make_potentials(nl)
-        for p in pots:
-            p.attach(state)
-        nl.compute(state)
-        # the list is frozen for the run: the per-step displacement check (a device->host flag
-        # read) belongs to the neighbour-list row, not to the force path that is timed here
-        nl.freeze()
-        torch.cuda.synchronize()
-        tuned = []
-        for p in pots:
-            if not args.no_tune:
-                tuned.append(p.tune_kernel_parameters(compute_virial=wl.compute_virial))
-            else:
-                p.kernel_parameters = (args.block, args.tpp)
-                tuned.append(p.kernel_parameters + (None,))
-
-        def step():
-            for p in pots:
-                p.compute(compute_virial=wl.compute_virial)
-
-        launches_per_step = len(pots)
-        n_local = n_total
-        n_bar = float(nl.n_neigh[:state.N].double().mean().item())
-        exchange_bytes = 0
-        sched = None
-    else:
-        from azplugins_b200 import slices
-
-        sched = slices.SliceScheduler.from_workload(wl, rank, world, dev, dtype=np.float32,
-                                                    buffer=synth.BUFFER, transport=args.transport)
-        if not args.no_tune:
-            tuned = sched.tune(compute_virial=wl.compute_virial)
-        else:
-            tuned = []
-        step = lambda: sched.step(compute_virial=wl.compute_virial)  # noqa: E731
-        launches_per_step = sched.launches_per_step
-        n_local = sched.n_local
-        n_bar = sched.mean_row_length()
-        exchange_bytes = sched.exchange_bytes_per_step()
-
-    def barrier():
-        if multi:
-            dist.barrier()
-        torch.cuda.synchronize()
-
+    job = Job(wl, args, torch, dist, dev, rank, world)
+    step, barrier = job.step, job.barrier
     for _ in range(W):
         step()
     barrier()
 
-    # ---- device-resident timing: K steps between two events on the launching stream -----------
-    def timed_region():
-        e0 = torch.cuda.Event(enable_timing=True)
-        e1 = torch.cuda.Event(enable_timing=True)
-        barrier()
-        e0.record()
-        for _ in range(K):
-            step()
-        e1.record()
-        barrier()
-        return e0.elapsed_time(e1)
-
+    # ---- device-resident timing, with the clocks sampled under the same load -----------------
     def load_probe():
         # same step, untimed; a fixed count so that every rank runs the same number of steps
         # (the multi-GPU step contains device barriers)
@@ -341,26 +456,20 @@ def run_b200(args):
             step()
         torch.cuda.synchronize()
 
-    # ~1 s of load from the warm-up's own timing (identical on every rank: all-reduced)
     t0 = time.perf_counter()
     for _ in range(3):
         step()
     torch.cuda.synchronize()
-    est = torch.tensor([(time.perf_counter() - t0) / 3.0], dtype=torch.float64, device=dev)
-    if multi:
-        dist.all_reduce(est, op=dist.ReduceOp.MAX)
-    probe_steps = int(min(20000, max(10, 1.0 / max(float(est.item()), 1e-6))))
-    ms_total, clocks = timed_with_clocks(timed_region, local_rank, load_probe)
+    est = job.max_over_ranks((time.perf_counter() - t0) / 3.0)[0]
+    probe_steps = int(min(20000, max(10, 1.0 / max(est, 1e-6))))
+    ms_total, clocks = timed_with_clocks(lambda: job.time_steps(K), local_rank, load_probe)
     clocks["sampled_over"] = "timed region + %d untimed repeats of the same step" % probe_steps
-    if multi:
-        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
     ms_step = ms_total / K
     value = n_total / (ms_step * 1e-3)
 
     # ---- end to end through the public API with host buffers --------------------------------
     if not multi:
+        state, pots = job.state, job.pots
         host_pos = torch.empty_like(state.pos, device="cpu").pin_memory()
         host_pos.copy_(state.pos)
         host_force = torch.empty_like(pots[0]._force, device="cpu").pin_memory()
@@ -377,78 +486,90 @@ def run_b200(args):
             for p in pots:
                 p.compute_to_host(host_force, host_virial if wl.compute_virial else None)
     else:
-        h2d, d2h = sched.e2e_bytes(wl.compute_virial)
-        e2e_step = lambda: sched.e2e_step(compute_virial=wl.compute_virial)  # noqa: E731
+        h2d, d2h = job.sched.e2e_bytes(wl.compute_virial)
+        e2e_step = lambda: job.sched.e2e_step(compute_virial=wl.compute_virial)  # noqa: E731
 
-    for _ in range(3):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    e0 = torch.cuda.Event(enable_timing=True)
-    e1 = torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(K):
-        e2e_step()
-    e1.record()
-    barrier()
-    e2e_ms = max(e0.elapsed_time(e1), 0.0)
-    e2e_wall_ms = (time.perf_counter() - t0) * 1e3
-    if multi:
-        t = torch.tensor([e2e_ms, e2e_wall_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms, e2e_wall_ms = float(t[0].item()), float(t[1].item())
-    e2e_value = n_total / (max(e2e_ms, e2e_wall_ms) / K * 1e-3)
+    e2e = None
+    if not args.no_e2e:
+        for _ in range(3):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            e2e_step()
+        e1.record()
+        barrier()
+        e2e_ms, e2e_wall_ms = job.max_over_ranks(max(e0.elapsed_time(e1), 0.0),
+                                                 (time.perf_counter() - t0) * 1e3)
+        e2e = {"value": n_total / (max(e2e_ms, e2e_wall_ms) / K * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": max(e2e_ms, e2e_wall_ms) / K}
 
-    # ---- roofline of the dominant kernel (per-rank: it processes n_local rows per launch) ------
-    # one launch per potential; time = device time of the step / launches (steps are kernel-only
-    # at N = 1; at N > 1 the step also holds the exchange, so the kernel is timed separately)
-    if multi:
-        kern_ms = sched.time_kernels(K, compute_virial=wl.compute_virial)
-        t = torch.tensor([kern_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        kern_ms = float(t.item())
-    else:
-        kern_ms = ms_step
-    # per potential: fixed arrays + the neighbour list once; a workload with two
-    # potentials (C3) streams the list twice, and the step time covers both launches
-    n_pot = len(wl.potentials)
-    bytes_fixed = wl.bytes_per_particle - 4.0 * wl.n_bar if wl.bytes_per_particle else 44.0
-    alg_bytes = (bytes_fixed + 4.0 * n_bar) * n_local * n_pot
-    achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": NCU_TRAFFIC_BYTES.get(args.workload),
-                "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
-                "kernel_ms": kern_ms, "algorithmic_bytes_per_step": alg_bytes,
-                "bytes_per_particle": (bytes_fixed + 4.0 * n_bar) * n_pot,
-                "mean_row_length": n_bar, "launches_per_step": launches_per_step}
-    if args.workload in NCU_WARP_INSTRUCTIONS and not multi and clocks.get("sm_mhz"):
-        # informational co-limiter: one warp instruction per scheduler per clock
-        floor_ms = (NCU_WARP_INSTRUCTIONS[args.workload] * (n_local / 1.0e6)
-                    / (SM_COUNT * SCHEDULERS_PER_SM * clocks["sm_mhz"] * 1e6) * 1e3)
-        roofline["issue_floor_ms"] = floor_ms
-        roofline["issue_frac"] = floor_ms / kern_ms
+    # ---- roofline of the dominant kernel (per rank: it processes n_local rows per launch) ------
+    kern_ms = job.kernel_ms(K) or ms_step
+    roofline = job.roofline(kern_ms, hbm_peak, peak_src)
+    entry, ncu_note, src_hash = ncu_constants(args.workload)
+    roofline["ncu_capture"] = ncu_note
+    roofline["kernel_sources"] = src_hash
+    if entry is not None and not multi and n_total == int(entry["N"]):
+        roofline["traffic"] = entry["dram_bytes"]
+        roofline["traffic_over_algorithmic"] = entry["dram_bytes"] / roofline["algorithmic_bytes_per_step"]
+        for k in ("l1_hit_pct", "l2_hit_pct", "issue_active_pct", "registers"):
+            if k in entry:
+                roofline[k] = entry[k]
+        if clocks.get("sm_mhz") and entry.get("warp_instructions"):
+            # informational co-limiter: one warp instruction per scheduler per clock
+            floor_ms = (entry["warp_instructions"]
+                        / (SM_COUNT * SCHEDULERS_PER_SM * clocks["sm_mhz"] * 1e6) * 1e3)
+            roofline["issue_floor_ms"] = floor_ms
+            roofline["issue_frac"] = floor_ms / kern_ms
+    check = job.check()
 
+    config = config_of(wl, world)
+    config.update({"mean_row_length": job.n_bar, "launch_shape_block_tpp_ms": job.tuned,
+                   "l2_policy": "inputs larger than L2: the %.0f MB neighbour list streams "
+                                "from HBM every step; positions stay L2-resident by design"
+                                % (4e-6 * job.n_bar * job.n_local),
+                   "parallelism": "1 GPU" if not multi else
+                   "%d particle slices, %s (%.1f MB/step/rank)"
+                   % (world, "halo pushed over NVLink peer memory" if job.sched.transport == "peer"
+                      else "NCCL halo exchange", job.exchange_bytes / 1e6)})
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl.name, "N": n_total, "particles_per_gpu": n_local,
-                       "types": len(wl.types), "mean_row_length": n_bar,
-                       "compute_virial": bool(wl.compute_virial),
-                       "launch_shape_block_tpp_ms": tuned,
-                       "l2_policy": "inputs larger than L2: the %.0f MB neighbour list streams "
-                                    "from HBM every step; positions stay L2-resident by design"
-                                    % (4e-6 * n_bar * n_local),
-                       "parallelism": "1 GPU" if not multi else
-                       "%d particle slices, %s (%.1f MB/step/rank)"
-                       % (world, "halo pushed over NVLink peer memory" if sched.transport == "peer"
-                          else "NCCL halo exchange", exchange_bytes / 1e6)},
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "roofline": roofline, "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": max(e2e_ms, e2e_wall_ms) / K},
-            "gpu_launches": launches_per_step * K}
+            "e2e": e2e, "gpu_launches": job.launches_per_step * K}
+    if check is not None:
+        line["check"] = check
+
+    # ---- the north star's scaling case in the same record: C5, N = 16 M in total, strong --------
+    if not args.no_strong and args.workload == "C2" and not args.n_per_gpu:
+        del job
+        torch.cuda.empty_cache()
+        wl5 = synth.config5(N=args.strong_n)
+        sj = Job(wl5, args, torch, dist, dev, rank, world)
+        for _ in range(W):
+            sj.step()
+        s_ms = sj.time_steps(K) / K
+        s_kern = sj.kernel_ms(K) or s_ms
+        s_roof = sj.roofline(s_kern, hbm_peak, peak_src)
+        line["strong_scaling"] = {
+            "workload": wl5.name, "N": wl5.N, "n_gpus": world, "ms_per_step": s_ms,
+            "value": wl5.N / (s_ms * 1e-3), "unit": UNIT, "scaling": "strong",
+            "kernel_ms": s_kern, "roofline_frac": s_roof["frac"],
+            "launch_shape_block_tpp_ms": sj.tuned, "check": sj.check(),
+            "note": "BASELINE.json north star: >= 6x at 8 GPUs for N = 16 M; the total N is fixed, "
+                    "so the speed-up is this value over the n_gpus = 1 run's"}
+        del sj
+        torch.cuda.empty_cache()
 
     if rank == 0 and not multi and not args.no_cpu_baseline:
-        _, info, _ = cpu_oracle_rate(wl, target_seconds=8.0)
+        from azplugins_b200.state import pack_pos
+
+        _, info, _ = cpu_oracle_rate(wl, pack_pos, target_seconds=15.0)
         line["cpu_baseline"] = info
     elif rank == 0:
         line["cpu_baseline"] = None

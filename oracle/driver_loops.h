@@ -14,6 +14,13 @@
 //
 // Full list (what the GPU classes use): each row owns its outputs, OpenMP over i is allowed.
 // Half list (what HOOMD's CPU classes use): Newton's third law to j < N, single thread.
+// half_list == 2, "domains" (the CPU baseline of bench.py): HOOMD's CPU parallelism is MPI domain
+// decomposition -- every rank runs the half-list loop over its own particles plus ghosts, so a
+// pair inside a domain is evaluated once and a pair across a domain face once on EACH side.
+// Restated with one OpenMP thread per domain over a FULL list: thread d owns the contiguous rows
+// [N d / D, N (d+1) / D) (a compact blob of the Morton-sorted particles); a neighbour j inside
+// the domain is taken only when j > i and receives the reaction, a neighbour outside is a
+// "ghost": evaluated, nothing written to it. No two threads write the same particle.
 #ifndef AZP_ORACLE_DRIVER_LOOPS_H_
 #define AZP_ORACLE_DRIVER_LOOPS_H_
 
@@ -173,12 +180,10 @@ template<class S, class Ad> void iso_loop(const PairArgs<S>& a, const void* para
     typedef typename Ad::param_type P;
     const P* params = static_cast<const P*>(params_v);
     zero_outputs(a);
-    const int nthreads = a.half_list ? 1 : (a.nthreads > 0 ? a.nthreads : 1);
+    const int nthreads = a.half_list == 1 ? 1 : (a.nthreads > 0 ? a.nthreads : 1);
     (void)nthreads;
-#pragma omp parallel for schedule(dynamic, 256) num_threads(nthreads)
-    for (long long ii = 0; ii < (long long)a.N; ++ii)
+    auto row = [&](const unsigned int i, const unsigned int dlo, const unsigned int dhi)
         {
-        const unsigned int i = (unsigned int)ii;
         const S* pi = a.pos + 4 * (size_t)i;
         const unsigned int ti = type_of(pi);
         S fx = 0, fy = 0, fz = 0, pe = 0;
@@ -188,6 +193,13 @@ template<class S, class Ad> void iso_loop(const PairArgs<S>& a, const void* para
         for (unsigned int k = 0; k < nn; ++k)
             {
             const unsigned int j = a.nlist[head + k];
+            bool react = a.half_list == 1 && j < a.N; // third law to the neighbour
+            if (a.half_list == 2)
+                {
+                react = j >= dlo && j < dhi;
+                if (react && j < i)
+                    continue; // pair inside the domain: taken from the lower index only
+                }
             const S* pj = a.pos + 4 * (size_t)j;
             const unsigned int tj = type_of(pj);
             S dx = pi[0] - pj[0], dy = pi[1] - pj[1], dz = pi[2] - pj[2];
@@ -239,7 +251,7 @@ template<class S, class Ad> void iso_loop(const PairArgs<S>& a, const void* para
             fy += dy * fdr;
             fz += dz * fdr;
             pe += eng * S(0.5);
-            if (a.half_list && j < a.N)
+            if (react)
                 {
                 S* fj = a.force + 4 * (size_t)j;
                 fj[0] -= dx * fdr;
@@ -259,7 +271,23 @@ template<class S, class Ad> void iso_loop(const PairArgs<S>& a, const void* para
         if (a.compute_virial)
             for (int c = 0; c < 6; ++c)
                 a.virial[c * a.virial_pitch + i] += w[c];
+        };
+    if (a.half_list == 2)
+        {
+        const int nd = a.nthreads > 0 ? a.nthreads : 1;
+#pragma omp parallel for schedule(static, 1) num_threads(nd)
+        for (int d = 0; d < nd; ++d)
+            {
+            const unsigned int dlo = (unsigned int)((unsigned long long)a.N * d / nd);
+            const unsigned int dhi = (unsigned int)((unsigned long long)a.N * (d + 1) / nd);
+            for (unsigned int i = dlo; i < dhi; ++i)
+                row(i, dlo, dhi);
+            }
+        return;
         }
+#pragma omp parallel for schedule(dynamic, 256) num_threads(nthreads)
+    for (long long ii = 0; ii < (long long)a.N; ++ii)
+        row((unsigned int)ii, 0u, 0u);
     }
 
 // ---------------------------------------------------------------------------------------------
@@ -272,12 +300,10 @@ template<class S, class Ad> void dpd_loop(const PairArgs<S>& a, const void* para
     typedef typename Ad::param_type P;
     const P* params = static_cast<const P*>(params_v);
     zero_outputs(a);
-    const int nthreads = a.half_list ? 1 : (a.nthreads > 0 ? a.nthreads : 1);
+    const int nthreads = a.half_list == 1 ? 1 : (a.nthreads > 0 ? a.nthreads : 1);
     (void)nthreads;
-#pragma omp parallel for schedule(dynamic, 256) num_threads(nthreads)
-    for (long long ii = 0; ii < (long long)a.N; ++ii)
+    auto row = [&](const unsigned int i, const unsigned int dlo, const unsigned int dhi)
         {
-        const unsigned int i = (unsigned int)ii;
         const S* pi = a.pos + 4 * (size_t)i;
         const S* vi = a.vel + 4 * (size_t)i;
         const unsigned int ti = type_of(pi);
@@ -288,6 +314,13 @@ template<class S, class Ad> void dpd_loop(const PairArgs<S>& a, const void* para
         for (unsigned int k = 0; k < nn; ++k)
             {
             const unsigned int j = a.nlist[head + k];
+            bool react = a.half_list == 1 && j < a.N; // third law to the neighbour
+            if (a.half_list == 2)
+                {
+                react = j >= dlo && j < dhi;
+                if (react && j < i)
+                    continue; // pair inside the domain: taken from the lower index only
+                }
             const S* pj = a.pos + 4 * (size_t)j;
             const S* vj = a.vel + 4 * (size_t)j;
             const unsigned int tj = type_of(pj);
@@ -334,7 +367,7 @@ template<class S, class Ad> void dpd_loop(const PairArgs<S>& a, const void* para
             fy += dy * fdr;
             fz += dz * fdr;
             pe += eng * S(0.5);
-            if (a.half_list && j < a.N)
+            if (react)
                 {
                 S* fj = a.force + 4 * (size_t)j;
                 fj[0] -= dx * fdr;
@@ -354,7 +387,23 @@ template<class S, class Ad> void dpd_loop(const PairArgs<S>& a, const void* para
         if (a.compute_virial)
             for (int c = 0; c < 6; ++c)
                 a.virial[c * a.virial_pitch + i] += w[c];
+        };
+    if (a.half_list == 2)
+        {
+        const int nd = a.nthreads > 0 ? a.nthreads : 1;
+#pragma omp parallel for schedule(static, 1) num_threads(nd)
+        for (int d = 0; d < nd; ++d)
+            {
+            const unsigned int dlo = (unsigned int)((unsigned long long)a.N * d / nd);
+            const unsigned int dhi = (unsigned int)((unsigned long long)a.N * (d + 1) / nd);
+            for (unsigned int i = dlo; i < dhi; ++i)
+                row(i, dlo, dhi);
+            }
+        return;
         }
+#pragma omp parallel for schedule(dynamic, 256) num_threads(nthreads)
+    for (long long ii = 0; ii < (long long)a.N; ++ii)
+        row((unsigned int)ii, 0u, 0u);
     }
 
 // ---------------------------------------------------------------------------------------------
@@ -366,12 +415,10 @@ template<class S, class Ad> void aniso_loop(const PairArgs<S>& a, const void* pa
     typedef typename Ad::param_type P;
     const P* params = static_cast<const P*>(params_v);
     zero_outputs(a);
-    const int nthreads = a.half_list ? 1 : (a.nthreads > 0 ? a.nthreads : 1);
+    const int nthreads = a.half_list == 1 ? 1 : (a.nthreads > 0 ? a.nthreads : 1);
     (void)nthreads;
-#pragma omp parallel for schedule(dynamic, 256) num_threads(nthreads)
-    for (long long ii = 0; ii < (long long)a.N; ++ii)
+    auto row = [&](const unsigned int i, const unsigned int dlo, const unsigned int dhi)
         {
-        const unsigned int i = (unsigned int)ii;
         const S* pi = a.pos + 4 * (size_t)i;
         const S* qi = a.orientation + 4 * (size_t)i;
         const unsigned int ti = type_of(pi);
@@ -382,6 +429,13 @@ template<class S, class Ad> void aniso_loop(const PairArgs<S>& a, const void* pa
         for (unsigned int k = 0; k < nn; ++k)
             {
             const unsigned int j = a.nlist[head + k];
+            bool react = a.half_list == 1 && j < a.N; // third law to the neighbour
+            if (a.half_list == 2)
+                {
+                react = j >= dlo && j < dhi;
+                if (react && j < i)
+                    continue; // pair inside the domain: taken from the lower index only
+                }
             const S* pj = a.pos + 4 * (size_t)j;
             const S* qj = a.orientation + 4 * (size_t)j;
             const unsigned int tj = type_of(pj);
@@ -418,7 +472,7 @@ template<class S, class Ad> void aniso_loop(const PairArgs<S>& a, const void* pa
             ty += t_i[1];
             tz += t_i[2];
             pe += eng * S(0.5);
-            if (a.half_list && j < a.N)
+            if (react)
                 {
                 S* fj = a.force + 4 * (size_t)j;
                 S* tqj = a.torque + 4 * (size_t)j;
@@ -446,7 +500,23 @@ template<class S, class Ad> void aniso_loop(const PairArgs<S>& a, const void* pa
         if (a.compute_virial)
             for (int c = 0; c < 6; ++c)
                 a.virial[c * a.virial_pitch + i] += w[c];
+        };
+    if (a.half_list == 2)
+        {
+        const int nd = a.nthreads > 0 ? a.nthreads : 1;
+#pragma omp parallel for schedule(static, 1) num_threads(nd)
+        for (int d = 0; d < nd; ++d)
+            {
+            const unsigned int dlo = (unsigned int)((unsigned long long)a.N * d / nd);
+            const unsigned int dhi = (unsigned int)((unsigned long long)a.N * (d + 1) / nd);
+            for (unsigned int i = dlo; i < dhi; ++i)
+                row(i, dlo, dhi);
+            }
+        return;
         }
+#pragma omp parallel for schedule(dynamic, 256) num_threads(nthreads)
+    for (long long ii = 0; ii < (long long)a.N; ++ii)
+        row((unsigned int)ii, 0u, 0u);
     }
     } // namespace azp_oracle
 

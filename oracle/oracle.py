@@ -373,7 +373,9 @@ class Oracle:
             a.periodic[d] = int(periodic[d])
         a.shift_mode = SHIFT_MODES[mode] if isinstance(mode, str) else int(mode)
         a.compute_virial = int(bool(virial))
-        a.half_list = int(bool(half))
+        # half: False (full list), True (half list, third law, one thread), "domains" (full list
+        # in, one half-list domain per thread: HOOMD's MPI decomposition; driver_loops.h)
+        a.half_list = 2 if half == "domains" else int(bool(half))
         a.rint_image = int(bool(rint_image))
         a.nthreads = nthreads if nthreads > 0 else self.max_threads()
         rc = np.broadcast_to(np.asarray(rcut, dtype=np.float64), (ntypes, ntypes))
@@ -382,7 +384,7 @@ class Oracle:
         ro = np.broadcast_to(np.asarray(ron, dtype=np.float64), (ntypes, ntypes))
         rosq = arr((ro.astype(dt) * ro.astype(dt)).reshape(-1), dt)
         a.ronsq = rosq.ctypes.data
-        n_out = pos.shape[0] if half else n_rows
+        n_out = pos.shape[0] if half is True else n_rows
         force = np.zeros((n_out, 4), dtype=dt)
         pitch = n_out
         vir = np.zeros((6, pitch), dtype=dt)

@@ -189,6 +189,45 @@ def test_half_list_equals_full_list(dtype):
 
 
 @pytest.mark.parametrize("dtype", DTYPES, ids=["f32", "f64"])
+@pytest.mark.parametrize("nthreads", [1, 3, 8])
+def test_domain_decomposed_half_list_equals_full_list(dtype, nthreads):
+    """half="domains" (bench.py's CPU baseline: one half-list domain per thread, HOOMD's MPI
+    decomposition restated over a full list) gives the full-list forces up to summation order,
+    for all three loops and any number of domains."""
+    orc = oracle.load("port", dtype)
+    pos, L, rng = random_system(1500, 0.7, 2, dtype, 9)
+    full = orc.build_nlist(pos, [L] * 3, 2.9, ntypes=2)
+    tol = 3e-4 if dtype == np.float32 else 1e-11
+
+    def close(a, b):
+        return np.abs(a - b).max() <= tol * max(1.0, np.abs(a).max())
+
+    yk = {(0, 0): dict(epsilon=1.0, kappa=1.0, delta=0.0), (0, 1): dict(epsilon=2.0, kappa=1.2, delta=0.15),
+          (1, 1): dict(epsilon=3.0, kappa=1.5, delta=0.3)}
+    t = orc.pack_table("ExpandedYukawa", 2, yk)
+    a = orc.pair_forces("ExpandedYukawa", t, pos, *full, [L] * 3, 2.5, ntypes=2, mode="shift")
+    b = orc.pair_forces("ExpandedYukawa", t, pos, *full, [L] * 3, 2.5, ntypes=2, mode="shift",
+                        half="domains", nthreads=nthreads)
+    assert close(a[0], b[0]) and close(a[1], b[1])
+    vel = np.zeros((len(pos), 4), dtype=dtype)
+    vel[:, :3] = rng.normal(size=(len(pos), 3))
+    tag = rng.permutation(len(pos)).astype(np.uint32)
+    dp = {k: dict(A=25.0, gamma=4.5, s=2.0) for k in yk}
+    t = orc.pack_table("DPDGeneralWeight", 2, dp)
+    a = orc.dpd_forces(t, pos, vel, tag, *full, [L] * 3, 1.9, 42, 1000, 0.01, 1.3, ntypes=2)
+    b = orc.dpd_forces(t, pos, vel, tag, *full, [L] * 3, 1.9, 42, 1000, 0.01, 1.3, ntypes=2,
+                       half="domains", nthreads=nthreads)
+    assert close(a[0], b[0]) and close(a[1], b[1])
+    q = rng.normal(size=(len(pos), 4))
+    q = (q / np.linalg.norm(q, axis=1, keepdims=True)).astype(dtype)
+    mp = {k: dict(M_d=1.8, M_r=0.3, r_eq=1.0, omega=5.0, alpha=0.5, repulsion=True) for k in yk}
+    t = orc.pack_table("TwoPatchMorse", 2, mp)
+    a = orc.aniso_forces(t, pos, q, *full, [L] * 3, 1.8, ntypes=2)
+    b = orc.aniso_forces(t, pos, q, *full, [L] * 3, 1.8, ntypes=2, half="domains", nthreads=nthreads)
+    assert all(close(x, y) for x, y in zip(a, b))
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=["f32", "f64"])
 def test_min_image_variants_agree(dtype):
     """Host (compare/subtract) and device (rint) minimum image agree away from exact ties."""
     orc = oracle.load("port", dtype)
