@@ -87,6 +87,8 @@ def parse():
                     help="multi-GPU halo transport: NVLink peer-memory push (default) or NCCL send/recv")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the e2e leg")
+    ap.add_argument("--cuda-profiler", action="store_true",
+                    help="bracket the timed region with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     ap.add_argument("--no-strong", action="store_true",
                     help="skip the C5 N = 16 M strong-scaling record appended to the C2 line")
     ap.add_argument("--strong-n", type=int, default=16000000)
@@ -462,7 +464,16 @@ def run_b200(args):
     torch.cuda.synchronize()
     est = job.max_over_ranks((time.perf_counter() - t0) / 3.0)[0]
     probe_steps = int(min(20000, max(10, 1.0 / max(est, 1e-6))))
-    ms_total, clocks = timed_with_clocks(lambda: job.time_steps(K), local_rank, load_probe)
+    def timed_region():
+        if args.cuda_profiler:
+            torch.cuda.cudart().cudaProfilerStart()
+        try:
+            return job.time_steps(K)
+        finally:
+            if args.cuda_profiler:
+                torch.cuda.cudart().cudaProfilerStop()
+
+    ms_total, clocks = timed_with_clocks(timed_region, local_rank, load_probe)
     clocks["sampled_over"] = "timed region + %d untimed repeats of the same step" % probe_steps
     ms_step = ms_total / K
     value = n_total / (ms_step * 1e-3)

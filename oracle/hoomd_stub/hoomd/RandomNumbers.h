@@ -1,6 +1,6 @@
 // TEST INFRASTRUCTURE (oracle). Not part of the product path.
 //
-// Host-only stand-in for the parts of HOOMD-blue v7.0.1 `hoomd/RandomNumbers.h` (+ the Random123
+// Stand-in (host + device under nvcc) for the parts of HOOMD-blue v7.0.1 `hoomd/RandomNumbers.h` (+ the Random123
 // Philox4x32-10 engine HOOMD vendors) used by reference
 // src/DPDPairEvaluatorGeneralWeight.h:226-233. Neither HOOMD nor Random123 is in the reference
 // tree, so this restates their published behaviour from scratch:
@@ -34,7 +34,7 @@ struct philox_u2
     uint32_t v[2];
     };
 
-inline philox_u4 philox4x32_10(philox_u4 ctr, philox_u2 key)
+AZP_STUB_HD inline philox_u4 philox4x32_10(philox_u4 ctr, philox_u2 key)
     {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
     const uint32_t W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
@@ -58,13 +58,13 @@ inline philox_u4 philox4x32_10(philox_u4 ctr, philox_u2 key)
 class Seed
     {
     public:
-    Seed(uint8_t id, uint64_t timestep, uint16_t seed)
+    AZP_STUB_HD Seed(uint8_t id, uint64_t timestep, uint16_t seed)
         {
         m_key.v[0] = (uint32_t(id) << 24) | (uint32_t(seed) << 8)
                      | uint32_t((timestep & 0x000000ff00000000ull) >> 32);
         m_key.v[1] = uint32_t(timestep & 0x00000000ffffffffull);
         }
-    const detail::philox_u2& getKey() const
+    AZP_STUB_HD const detail::philox_u2& getKey() const
         {
         return m_key;
         }
@@ -76,14 +76,14 @@ class Seed
 class Counter
     {
     public:
-    Counter(uint32_t a = 0, uint32_t b = 0, uint32_t c = 0, uint16_t d = 0)
+    AZP_STUB_HD Counter(uint32_t a = 0, uint32_t b = 0, uint32_t c = 0, uint16_t d = 0)
         {
         m_ctr.v[0] = uint32_t(d) << 16;
         m_ctr.v[1] = c;
         m_ctr.v[2] = b;
         m_ctr.v[3] = a;
         }
-    const detail::philox_u4& getCounter() const
+    AZP_STUB_HD const detail::philox_u4& getCounter() const
         {
         return m_ctr;
         }
@@ -95,11 +95,11 @@ class Counter
 class RandomGenerator
     {
     public:
-    RandomGenerator(const Seed& seed, const Counter& counter)
+    AZP_STUB_HD RandomGenerator(const Seed& seed, const Counter& counter)
         : m_key(seed.getKey()), m_ctr(counter.getCounter())
         {
         }
-    detail::philox_u4 operator()()
+    AZP_STUB_HD detail::philox_u4 operator()()
         {
         detail::philox_u4 u = detail::philox4x32_10(m_ctr, m_key);
         m_ctr.v[0] += 1;
@@ -113,23 +113,23 @@ class RandomGenerator
 
 namespace detail
     {
-inline uint32_t generate_u32(RandomGenerator& rng)
+AZP_STUB_HD inline uint32_t generate_u32(RandomGenerator& rng)
     {
     return rng().v[0];
     }
-inline uint64_t generate_u64(RandomGenerator& rng)
+AZP_STUB_HD inline uint64_t generate_u64(RandomGenerator& rng)
     {
     philox_u4 u = rng();
     return (uint64_t(u.v[0]) << 32) | u.v[1];
     }
-template<class Real> inline Real generate_canonical(RandomGenerator& rng);
-template<> inline float generate_canonical<float>(RandomGenerator& rng)
+template<class Real> AZP_STUB_HD inline Real generate_canonical(RandomGenerator& rng);
+template<> AZP_STUB_HD inline float generate_canonical<float>(RandomGenerator& rng)
     {
     const float factor = 1.0f / (4294967295.0f + 1.0f); // 2^-32
     const float halffactor = 0.5f * factor;
     return float(generate_u32(rng)) * factor + halffactor;
     }
-template<> inline double generate_canonical<double>(RandomGenerator& rng)
+template<> AZP_STUB_HD inline double generate_canonical<double>(RandomGenerator& rng)
     {
     const double factor = 1.0 / (18446744073709551615.0 + 1.0); // 2^-64
     const double halffactor = 0.5 * factor;
@@ -140,8 +140,8 @@ template<> inline double generate_canonical<double>(RandomGenerator& rng)
 template<class Real> class UniformDistribution
     {
     public:
-    UniformDistribution(Real a = Real(0), Real b = Real(1)) : m_a(a), m_width(b - a) { }
-    Real operator()(RandomGenerator& rng)
+    AZP_STUB_HD UniformDistribution(Real a = Real(0), Real b = Real(1)) : m_a(a), m_width(b - a) { }
+    AZP_STUB_HD Real operator()(RandomGenerator& rng)
         {
         return m_a + m_width * detail::generate_canonical<Real>(rng);
         }

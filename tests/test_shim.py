@@ -32,11 +32,31 @@ def test_shim_compiles_and_links(tmp_path):
 
 
 @pytest.mark.gpu
-def test_shim_reproduces_reference_kat(tmp_path):
+def test_shim_reproduces_reference_kats(tmp_path):
+    """All three HOOMD driver templates, instantiated like the reference's *.cu.inc stubs do
+    (src/PotentialPairGPUKernel.cu.inc:25-28, src/PotentialPairDPDThermoGPUKernel.cu.inc:21-24,
+    src/AnisoPotentialPairGPUKernel.cu.inc:21-25), reproduce reference known answers
+    (src/pytest/test_pair.py:76-85,177-186, src/pytest/test_pair_aniso.py:22-40)."""
     exe = build(tmp_path)
-    out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()
-    vals = dict(zip(out[0::2], out[1::2])) if False else out
-    assert out[0] == "rc" and out[1] == "0"
-    f0x, e0, f1x, e1 = float(out[3]), float(out[7]), float(out[9]), float(out[11])
-    assert abs(f0x + 0.5477) < 1.5e-4 and abs(f1x - 0.5477) < 1.5e-4
-    assert abs(e0 - 0.0985 / 2) < 1.5e-4 and abs(e1 - 0.0985 / 2) < 1.5e-4
+    lines = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.splitlines()
+    got = {ln.split()[0]: ln.split()[1:] for ln in lines}
+    assert set(got) == {"hertz", "dpd", "morse"}
+    for name, U, F in (("hertz", 0.0985, 0.5477), ("dpd", 0.25, 1.0)):
+        out = got[name]
+        assert out[0] == "rc" and out[1] == "0"
+        f0x, e0, f1x, e1 = float(out[3]), float(out[7]), float(out[9]), float(out[11])
+        assert abs(f0x + F) < 1.5e-4 and abs(f1x - F) < 1.5e-4, name
+        assert abs(e0 - U / 2) < 1.5e-4 and abs(e1 - U / 2) < 1.5e-4, name
+    out = got["morse"]
+    assert out[1] == "0"
+    f0 = [float(x) for x in out[3:6]]
+    e0, f1x, e1 = float(out[7]), float(out[9]), float(out[11])
+    t0 = [float(x) for x in out[13:16]]
+    t1 = [float(x) for x in out[17:20]]
+    for a, b in zip(f0, (11.75766, 2.46991, 3.70487)):
+        assert abs(a - b) < 1.5e-4
+    assert abs(f1x + 11.75766) < 1.5e-4
+    assert abs(e0 + 0.41134 / 2) < 1.5e-4 and abs(e1 + 0.41134 / 2) < 1.5e-4
+    for t in (t0, t1):
+        for a, b in zip(t, (0.0, -0.08879, 0.05919)):
+            assert abs(a - b) < 1.5e-4
