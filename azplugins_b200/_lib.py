@@ -162,6 +162,8 @@ EXPORTED_SYMBOLS = (
     "azp_dpd_forces_f64",
     "azp_aniso_forces_f32",
     "azp_aniso_forces_f64",
+    "azp_pair_forces_fused_f32",
+    "azp_pair_forces_fused_f64",
     "azp_autotune",
     "azp_gather_rows",
     "azp_push_rows",
@@ -218,6 +220,11 @@ def _load():
     for name in ("azp_aniso_forces_f32", "azp_aniso_forces_f64"):
         getattr(lib, name).argtypes = [i32, ctypes.POINTER(AzpPairArgs), vp, vp, vp]
         getattr(lib, name).restype = i32
+    for name in ("azp_pair_forces_fused_f32", "azp_pair_forces_fused_f64"):
+        if hasattr(lib, name):  # absent from pre-fusion A/B builds loaded through AZP_B200_LIB
+            getattr(lib, name).argtypes = [i32, ctypes.POINTER(AzpPairArgs), vp, i32,
+                                           ctypes.POINTER(AzpPairArgs), vp, vp]
+            getattr(lib, name).restype = i32
     lib.azp_autotune.argtypes = [i32, i32, i32, ctypes.POINTER(AzpPairArgs), vp, vp,
                                  ctypes.POINTER(u32), ctypes.POINTER(u32),
                                  ctypes.POINTER(ctypes.c_float)]

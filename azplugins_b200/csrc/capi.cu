@@ -34,6 +34,9 @@ extern template cudaError_t launch_dpd<DPDPairEvaluatorGeneralWeight<double>, do
 extern template cudaError_t launch_aniso<AnisoPairEvaluatorTwoPatchMorse<float>, float>(const azp_pair_args*, const void*, cudaStream_t);
 extern template cudaError_t launch_aniso<AnisoPairEvaluatorTwoPatchMorse<double>, double>(const azp_pair_args*, const void*, cudaStream_t);
 
+extern template cudaError_t launch_pair_fused<PairEvaluatorColloid<float>, PairEvaluatorHertz<float>, float>(const azp_pair_args*, const void*, const azp_pair_args*, const void*, cudaStream_t);
+extern template cudaError_t launch_pair_fused<PairEvaluatorColloid<double>, PairEvaluatorHertz<double>, double>(const azp_pair_args*, const void*, const azp_pair_args*, const void*, cudaStream_t);
+
 template<class S> static cudaError_t dispatch_pair(int ev, const azp_pair_args* a, const void* p, cudaStream_t st)
     {
     switch (ev)
@@ -287,6 +290,18 @@ extern "C"
     int azp_pair_forces_f64(int ev, const azp_pair_args* a, const void* p, void* stream)
         {
         return run_family(0, ev, 64, a, p, (cudaStream_t)stream);
+        }
+    int azp_pair_forces_fused_f32(int ev_a, const azp_pair_args* a, const void* pa, int ev_b, const azp_pair_args* b, const void* pb, void* stream)
+        {
+        if (ev_a == AZP_EV_COLLOID && ev_b == AZP_EV_HERTZ)
+            return (int)launch_pair_fused<PairEvaluatorColloid<float>, PairEvaluatorHertz<float>, float>(a, pa, b, pb, (cudaStream_t)stream);
+        return (int)cudaErrorNotSupported;
+        }
+    int azp_pair_forces_fused_f64(int ev_a, const azp_pair_args* a, const void* pa, int ev_b, const azp_pair_args* b, const void* pb, void* stream)
+        {
+        if (ev_a == AZP_EV_COLLOID && ev_b == AZP_EV_HERTZ)
+            return (int)launch_pair_fused<PairEvaluatorColloid<double>, PairEvaluatorHertz<double>, double>(a, pa, b, pb, (cudaStream_t)stream);
+        return (int)cudaErrorNotSupported;
         }
     int azp_dpd_forces_f32(int ev, const azp_pair_args* a, const void* p, void* stream)
         {

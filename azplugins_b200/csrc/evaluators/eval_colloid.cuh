@@ -221,5 +221,21 @@ template<class S> class PairEvaluatorColloid : public PairEvaluatorBase<S>
     private:
     const cache_type& c;
     };
+#if defined(AZP_COLLOID_PIPE0) || defined(AZP_COLLOID_SMEM)
+template<class E> struct IsoTraits;
+template<class S> struct IsoTraits<PairEvaluatorColloid<S>>
+    {
+#ifdef AZP_COLLOID_PIPE0
+    static constexpr int pipe = 0;
+#else
+    static constexpr int pipe = 2;
+#endif
+#ifdef AZP_COLLOID_SMEM
+    static constexpr bool register_tables = false;
+#else
+    static constexpr bool register_tables = true;
+#endif
+    };
+#endif
     } // namespace azp
 #endif

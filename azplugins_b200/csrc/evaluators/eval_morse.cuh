@@ -134,13 +134,19 @@ template<class S> class AnisoPairEvaluatorTwoPatchMorse
     // body of evaluate() for a pair already known to satisfy rsq <= rcutsq
     AZP_D void evaluatePair(S rsq, Vec3<S>& force, S& pair_eng, bool, Vec3<S>& torque_i, Vec3<S>& torque_j)
         {
-        // The well exp(-(r - r_eq) / M_r) (M_r = 0.03: one ulp of r is 3e-6 of U) and the patch
-        // switch Omega(gamma) (omega = 20) amplify the fp32 rounding of r, rhat, n and gamma
-        // beyond the parity budget, so everything up to Omega follows the reference's host
-        // sequence rounding for rounding (azp_core.cuh, namespace ref): rsq = dot(dr, dr),
-        // rinv = 1 / sqrt(rsq), r = 1 / rinv (:137-139), rhat = dr * rinv, gamma = dot(rhat, n),
-        // exp() of the math library, Omega = 1 / (1 + e) as an IEEE division. (The argument
-        // rsq of this function was accumulated with FMAs for the cutoff test.)
+        // The well exp(-(r - r_eq) / M_r) (M_r = 0.03: one ulp of r is 3e-6 of U, 6e-6 of its
+        // repulsive wall) amplifies the fp32 rounding of r beyond the parity budget, and the
+        // patch switch Omega(gamma) (omega = 20) that of gamma. The CPU reference's own fp32
+        // result is farther from the exact one than the budget, so "more accurate" does not
+        // help: r and gamma are rounded exactly where the reference's host code rounds them
+        // (azp_core.cuh, namespace ref): rsq = dot(dr, dr) without FMA, rinv = 1 / sqrt(rsq),
+        // r = 1 / rinv (:137-139), rhat = dr * rinv, n = rotate(q, ex), gamma = dot(rhat, n),
+        // and the radial exponential is the math library's expf. (The argument rsq of this
+        // function was accumulated with FMAs for the cutoff test.) Everything after that --
+        // Omega's exponential and reciprocal, the force and torque assembly -- is not
+        // amplified and uses the SFU approximations and contracted FMAs
+        // (AZP_MORSE_FULL_REF: library exp and IEEE reciprocal there too, +18 % time on C5, kept
+        // for A/B measurements).
         S r, rinv;
         ref::r_and_rinv(ref::dot3(dr.x, dr.y, dr.z, dr.x, dr.y, dr.z), r, rinv);
         const Vec3<S> u {ref::mul(dr.x, rinv), ref::mul(dr.y, rinv), ref::mul(dr.z, rinv)};
@@ -157,26 +163,35 @@ template<class S> class AnisoPairEvaluatorTwoPatchMorse
             dUM = S(2.0) * c.M_d * c.M_rinv * me * om;
             }
         const S gi = ref::dot3(u.x, u.y, u.z, ni.x, ni.y, ni.z);
+        const S gj = ref::dot3(u.x, u.y, u.z, nj.x, nj.y, nj.z);
+#ifdef AZP_MORSE_FULL_REF
         const S gie = ref::exp(ref::mul(-c.omega, ref::sub(ref::mul(gi, gi), c.alpha)));
         const S Oi = ref::rcp(ref::add(S(1.0), gie));
-        const S gj = ref::dot3(u.x, u.y, u.z, nj.x, nj.y, nj.z);
         const S gje = ref::exp(ref::mul(-c.omega, ref::sub(ref::mul(gj, gj), c.alpha)));
         const S Oj = ref::rcp(ref::add(S(1.0), gje));
+#else
+        const S gie = fast::exp(ref::mul(-c.omega, ref::sub(ref::mul(gi, gi), c.alpha)));
+        const S Oi = fast::rcp(S(1.0) + gie);
+        const S gje = fast::exp(ref::mul(-c.omega, ref::sub(ref::mul(gj, gj), c.alpha)));
+        const S Oj = fast::rcp(S(1.0) + gje);
+#endif
 
         const S OiOj = Oi * Oj;
         const S dU_dr = dUM * OiOj;
         const S dU_dgi = (S(2.0) * c.omega * gi * gie * Oi * Oi) * UM * Oj;
         const S dU_dgj = (S(2.0) * c.omega * gj * gje * Oj * Oj) * UM * Oi;
 
-        // u x n and the in-plane director  n_perp = -u x (u x n) = n - (u.n) u
+        // u x n (the torque direction) and the in-plane director
+        // n_perp = -u x (u x n) = n - (u.n) u = n - gamma u   (|u| = 1)
         const Vec3<S> ci {u.y * ni.z - u.z * ni.y, u.z * ni.x - u.x * ni.z, u.x * ni.y - u.y * ni.x};
         const Vec3<S> cj {u.y * nj.z - u.z * nj.y, u.z * nj.x - u.x * nj.z, u.x * nj.y - u.y * nj.x};
-        const Vec3<S> pi {ci.y * u.z - ci.z * u.y, ci.z * u.x - ci.x * u.z, ci.x * u.y - ci.y * u.x};
-        const Vec3<S> pj {cj.y * u.z - cj.z * u.y, cj.z * u.x - cj.x * u.z, cj.x * u.y - cj.y * u.x};
+        const Vec3<S> pi {fma(-gi, u.x, ni.x), fma(-gi, u.y, ni.y), fma(-gi, u.z, ni.z)};
+        const Vec3<S> pj {fma(-gj, u.x, nj.x), fma(-gj, u.y, nj.y), fma(-gj, u.z, nj.z)};
 
-        force.x = -dU_dr * u.x - rinv * (dU_dgi * pi.x + dU_dgj * pj.x);
-        force.y = -dU_dr * u.y - rinv * (dU_dgi * pi.y + dU_dgj * pj.y);
-        force.z = -dU_dr * u.z - rinv * (dU_dgi * pi.z + dU_dgj * pj.z);
+        const S ai = rinv * dU_dgi, aj = rinv * dU_dgj;
+        force.x = -(dU_dr * u.x + (ai * pi.x + aj * pj.x));
+        force.y = -(dU_dr * u.y + (ai * pi.y + aj * pj.y));
+        force.z = -(dU_dr * u.z + (ai * pi.z + aj * pj.z));
         torque_i = Vec3<S> {dU_dgi * ci.x, dU_dgi * ci.y, dU_dgi * ci.z};
         torque_j = Vec3<S> {dU_dgj * cj.x, dU_dgj * cj.y, dU_dgj * cj.z};
         pair_eng = (UM - c.U_cut) * OiOj;

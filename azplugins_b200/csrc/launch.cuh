@@ -18,6 +18,11 @@ namespace azp
 // ---- long-row deferral scratch: one small queue per (device, stream), allocated on first use --
 constexpr unsigned int kLongRowThreshold = 512; // rows longer than this go to the second pass
 constexpr unsigned int kLongRowCapacity = 1u << 16;
+#ifndef AZP_ROWS_PER_GROUP
+#define AZP_ROWS_PER_GROUP 1
+#endif
+constexpr unsigned int kRowsPerGroup = AZP_ROWS_PER_GROUP;
+constexpr double kShortRow = 64.0; // mean row capacity up to which rows count as short
 struct LongRowScratch
     {
     unsigned int* queue = nullptr;
@@ -75,6 +80,11 @@ template<class S> inline KernelArgs<S> convert_args(const azp_pair_args& a)
     k.long_count = nullptr;
     k.long_capacity = 0;
     k.long_threshold = kLongRowThreshold;
+    k.force_b = nullptr;
+    k.virial_b = nullptr;
+    k.rcutsq_b = nullptr;
+    k.params_b = nullptr;
+    k.shift_mode_b = 0;
     return k;
     }
 
@@ -120,7 +130,16 @@ inline cudaError_t choose_shape(const azp_pair_args& a, LaunchShape& s, unsigned
         ++lg;
     const unsigned long long nslots = a.d_row_ids ? a.n_row_ids : a.N;
     const unsigned long long threads = nslots * tpp;
-    const unsigned long long grid = (threads + block - 1) / block;
+    // rows per group of tpp lanes (row_kernel's main pass walks slot, slot + G, ...): one for
+    // long rows; short rows (mean capacity <= kShortRow) take kRowsPerGroup rows per group with
+    // the next row's metadata and list line prefetched -- never fewer CTAs than fill the machine
+    unsigned long long grid = (threads + block - 1) / block;
+    const double mean_cap_rows = a.size_neigh_list && a.N ? double(a.size_neigh_list) / a.N : 1e9;
+    if (kRowsPerGroup > 1 && mean_cap_rows <= kShortRow)
+        {
+        const unsigned long long g = (grid + kRowsPerGroup - 1) / kRowsPerGroup;
+        grid = g > 148ull * 16ull ? g : (grid < 148ull * 16ull ? grid : 148ull * 16ull);
+        }
     if (grid > 0x7fffffffull)
         return cudaErrorInvalidValue;
     s.block = block;
@@ -221,7 +240,7 @@ template<class E, class S> cudaError_t launch_pair(const azp_pair_args* a, const
         return err;
     const KernelArgs<S> k = convert_args<S>(*a);
     const bool xplor = a->shift_mode == 2, vir = a->compute_virial != 0;
-    const int ntm = a->ntypes == 1 ? 1 : (a->ntypes == 2 ? 2 : 0);
+    const int ntm = a->ntypes == 1 ? 1 : (a->ntypes == 2 && IsoTraits<E>::register_tables ? 2 : 0);
 #define AZP_CASE(X, V, T)           \
     if (xplor == X && vir == V && ntm == T) \
         return launch_pair_variant<E, S, X, V, T>(k, d_params, s, a->n_max, stream);
@@ -237,6 +256,51 @@ template<class E, class S> cudaError_t launch_pair(const azp_pair_args* a, const
     AZP_CASE(true, true, 0)
     AZP_CASE(true, true, 1)
     AZP_CASE(true, true, 2)
+#undef AZP_CASE
+    return cudaErrorInvalidValue;
+    }
+
+// Two isotropic potentials over one sweep of the list (FusedIsoFamily). `a` and `b` must describe
+// the same rows, particles and list; outputs, cutoffs, parameters and shift mode (none / shift)
+// are per potential. Launch shape and row selection are taken from `a`.
+template<class EA, class EB, class S>
+cudaError_t launch_pair_fused(const azp_pair_args* a, const void* d_params_a, const azp_pair_args* b, const void* d_params_b, cudaStream_t stream)
+    {
+    cudaError_t err = check_common(a, d_params_a);
+    if (err == cudaSuccess)
+        err = check_common(b, d_params_b);
+    if (err != cudaSuccess)
+        return err;
+    if (a->shift_mode > 1 || b->shift_mode > 1)
+        return cudaErrorNotSupported; // xplor: evaluate the two potentials separately
+    if (a->d_pos != b->d_pos || a->d_n_neigh != b->d_n_neigh || a->d_nlist != b->d_nlist
+        || a->d_head_list != b->d_head_list || a->N != b->N || a->ntypes != b->ntypes
+        || a->row_offset != b->row_offset || a->d_row_ids != b->d_row_ids || a->n_row_ids != b->n_row_ids
+        || a->compute_virial != b->compute_virial || a->virial_pitch != b->virial_pitch)
+        return cudaErrorInvalidValue;
+    if (nothing_to_do(a))
+        return cudaSuccess;
+    LaunchShape s;
+    err = choose_shape(*a, s, max_block<S>());
+    if (err != cudaSuccess)
+        return err;
+    KernelArgs<S> k = convert_args<S>(*a);
+    k.force_b = static_cast<S*>(b->d_force);
+    k.virial_b = static_cast<S*>(b->d_virial);
+    k.rcutsq_b = static_cast<const S*>(b->d_rcutsq);
+    k.params_b = d_params_b;
+    k.shift_mode_b = b->shift_mode;
+    const bool vir = a->compute_virial != 0;
+    const int ntm = a->ntypes == 1 ? 1 : (a->ntypes == 2 ? 2 : 0);
+#define AZP_CASE(V, T)        \
+    if (vir == V && ntm == T) \
+        return launch_rows<FusedIsoFamily<EA, EB, S, V, T>>(k, d_params_a, s, a->n_max, stream);
+    AZP_CASE(false, 0)
+    AZP_CASE(false, 1)
+    AZP_CASE(false, 2)
+    AZP_CASE(true, 0)
+    AZP_CASE(true, 1)
+    AZP_CASE(true, 2)
 #undef AZP_CASE
     return cudaErrorInvalidValue;
     }

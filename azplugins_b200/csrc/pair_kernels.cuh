@@ -70,6 +70,13 @@ template<class S> struct KernelArgs
     unsigned int* long_count;
     unsigned int long_capacity;
     unsigned int long_threshold;
+    // second potential of a fused two-potential pass (FusedIsoFamily): own outputs and tables,
+    // same particles and list
+    S* force_b;
+    S* virial_b;
+    const S* rcutsq_b;
+    const void* params_b;
+    unsigned int shift_mode_b;
     };
 
 // largest block_size accepted: 512 threads (<= 128 registers) for fp32; the fp64 variants hold
@@ -151,19 +158,21 @@ extern __shared__ __align__(16) unsigned char azp_smem[];
 template<class E, class S> struct PairTable
     {
     typedef typename E::cache_type Cache;
-    unsigned int rcutsq_off; // byte offset of rcutsq[] (the cache array starts at 0)
+    unsigned int base_off;   // byte offset of the cache array (0 unless a second table follows)
+    unsigned int rcutsq_off; // byte offset of rcutsq[]
 
     AZP_HD static size_t bytes(size_t ntp)
         {
         return ntp * sizeof(Cache) + (ntp + 1) * sizeof(S);
         }
-    AZP_D void carve(unsigned int ntp)
+    AZP_D void carve(unsigned int ntp, unsigned int base = 0u)
         {
-        rcutsq_off = ntp * (unsigned int)sizeof(Cache);
+        base_off = base;
+        rcutsq_off = base + ntp * (unsigned int)sizeof(Cache);
         }
     AZP_D Cache& cache(unsigned int t) const
         {
-        return reinterpret_cast<Cache*>(azp_smem)[t];
+        return reinterpret_cast<Cache*>(azp_smem + base_off)[t];
         }
     // effective r_cut^2: 0 for pairs whose potential is switched off
     AZP_D S& rcutsq(unsigned int t) const
@@ -220,7 +229,10 @@ template<class C> AZP_D C select_words(bool pick_b, const C& a, const C& b)
 // Layout: slot s of thread t at word s * blockDim.x + t (conflict-free).
 struct AcceptQueue
     {
-    static constexpr unsigned int Q = 8;    // slots per lane
+#ifndef AZP_QUEUE_SLOTS
+#define AZP_QUEUE_SLOTS 8
+#endif
+    static constexpr unsigned int Q = AZP_QUEUE_SLOTS; // slots per lane
     static constexpr unsigned int ROOM = 4; // a trip pushes at most 4 entries per lane
     unsigned int n = 0;
     unsigned int off; // byte offset into azp_smem
@@ -334,13 +346,23 @@ template<class E, class S, int NTM> struct TypeLookup
 // =============================================================================================
 // Isotropic family: F_i = sum dx * force_divr, E_i = 1/2 sum U, W_i = 1/2 sum dx_a dx_b force_divr
 // =============================================================================================
+// Per-evaluator tuning traits of the isotropic family (defaults; an evaluator header may
+// specialise them): software-pipeline depth of the neighbour loop (2: index vector two trips and
+// gathers one trip ahead; 0: load, gather, compute in program order with the smallest register
+// footprint) and whether a two-type system keeps its candidate constants in registers.
+template<class E> struct IsoTraits
+    {
+    static constexpr int pipe = 2;
+    static constexpr bool register_tables = true;
+    };
+
 template<class E_, class S_, bool XPLOR, bool VIRIAL, int NTM_> struct IsoFamily
     {
     typedef E_ E;
     typedef S_ S;
     typedef typename E::cache_type Cache;
     static constexpr int NTM = NTM_;
-    static constexpr int PIPE = 2;
+    static constexpr int PIPE = IsoTraits<E>::pipe;
     static constexpr bool QUEUE = false;
 
     TypeLookup<E, S, NTM> types;
@@ -501,6 +523,163 @@ template<class E_, class S_, bool XPLOR, bool VIRIAL, int NTM_> struct IsoFamily
     };
 
 // =============================================================================================
+// Fused two-potential isotropic family: two evaluators over ONE sweep of
+// the neighbour list -- the reference's documented use is pair.Colloid plus pair.Hertz on the
+// same nlist (src/pair.py:66-76), two ForceComputes that each stream the whole list. One gather,
+// one displacement and one r^2 per neighbour feed both evaluators; each potential keeps its own
+// type-pair table (own r_cut^2: a pair may be inside one cutoff and outside the other), its own
+// accumulators and its own outputs, so the read-outs are those of two separate launches, bit for
+// bit. Modes none / shift (xplor falls back to separate launches).
+// =============================================================================================
+template<class EA, class EB, class S_, bool VIRIAL, int NTM_> struct FusedIsoFamily
+    {
+    typedef EA E; // the params pointer of the launch is potential A's
+    typedef S_ S;
+    static constexpr int NTM = NTM_;
+    static constexpr int PIPE = 2;
+    static constexpr bool QUEUE = false;
+
+    TypeLookup<EA, S, NTM> types; // potential A (row_kernel reads rc_max through it: see stage)
+    TypeLookup<EB, S, NTM> types_b;
+    S fx = S(0), fy = S(0), fz = S(0), pe = S(0);
+    S gx = S(0), gy = S(0), gz = S(0), qe = S(0);
+    Virial6<S> w, w_b;
+
+    AZP_HD static size_t smem_bytes(size_t ntp, size_t)
+        {
+        return PairTable<EA, S>::bytes(ntp) + 16 + PairTable<EB, S>::bytes(ntp) + 32;
+        }
+
+    AZP_D void stage(const KernelArgs<S>& a, const typename EA::param_type* params, unsigned int ntp)
+        {
+        PairTable<EA, S>& ta = types.tab;
+        PairTable<EB, S>& tb = types_b.tab;
+        ta.carve(ntp);
+        tb.carve(ntp, (ta.end_off(ntp) + 15u) & ~15u);
+        const typename EB::param_type* params_b = static_cast<const typename EB::param_type*>(a.params_b);
+        for (unsigned int t = threadIdx.x; t < ntp; t += blockDim.x)
+            {
+            const S rca = a.rcutsq[t], rcb = a.rcutsq_b[t];
+            const typename EA::cache_type ca = EA::make_cache(params[t], rca, a.shift_mode == 1);
+            const typename EB::cache_type cb = EB::make_cache(params_b[t], rcb, a.shift_mode_b == 1);
+            ta.cache(t) = ca;
+            ta.rcutsq(t) = EA::disabled(ca) ? S(0) : rca;
+            tb.cache(t) = cb;
+            tb.rcutsq(t) = EB::disabled(cb) ? S(0) : rcb;
+            }
+        __syncthreads();
+        ta.finish(ntp);
+        tb.finish(ntp);
+        __syncthreads();
+        // the interior-warp test of process_row reads rc_max of table A: make it the larger one
+        if (threadIdx.x == 0)
+            ta.rcutsq(ntp) = fmax(ta.rcutsq(ntp), tb.rcutsq(ntp));
+        __syncthreads();
+        types.after_stage();
+        types_b.after_stage();
+        }
+
+    AZP_D void begin_row(const KernelArgs<S>& a, unsigned int, unsigned int ti)
+        {
+        types.begin_row(ti, a.ntypes);
+        types_b.begin_row(ti, a.ntypes);
+        }
+    // row_kernel skips a row only when BOTH potentials are switched off for its particle type
+    struct BothOff
+        {
+        };
+
+    struct Head
+        {
+        S dx, dy, dz;
+        unsigned int tj;
+        };
+    AZP_D Head head(const KernelArgs<S>& a, const RowGeometry<S>& g, unsigned int, const Vec4<S>& pj) const
+        {
+        Head h;
+        g.displacement(a.box, pj, h.dx, h.dy, h.dz);
+        h.tj = NTM == 1 ? 0u : scalar_as_uint(pj.w);
+        return h;
+        }
+    AZP_D void pair(const KernelArgs<S>& a, const RowGeometry<S>& g, unsigned int j, const Vec4<S>& pj)
+        {
+        body(a, head(a, g, j, pj));
+        }
+    template<class EX, class TL>
+    AZP_D void one(const TL& tl, S rsq, unsigned int tj, S dx, S dy, S dz, S& ax, S& ay, S& az, S& ae, Virial6<S>& aw)
+        {
+        const S rcutsq = tl.rcutsq(tj);
+        const bool inside = rsq < rcutsq;
+        if (EX::kWarpVote && __ballot_sync(__activemask(), inside) == 0u)
+            return;
+        const typename EX::cache_type c = tl.cache(tj);
+        S f = S(0), e = S(0);
+        EX eval(rsq, rcutsq, c);
+        eval.evalPair(f, e, false);
+        const S force_divr = inside ? f : S(0);
+        const S pair_eng = inside ? e : S(0);
+        ax = fma(dx, force_divr, ax);
+        ay = fma(dy, force_divr, ay);
+        az = fma(dz, force_divr, az);
+        ae += pair_eng;
+        if (VIRIAL)
+            {
+            const S vx = dx * force_divr, vy = dy * force_divr, vz = dz * force_divr;
+            aw.xx = fma(dx, vx, aw.xx);
+            aw.xy = fma(dx, vy, aw.xy);
+            aw.xz = fma(dx, vz, aw.xz);
+            aw.yy = fma(dy, vy, aw.yy);
+            aw.yz = fma(dy, vz, aw.yz);
+            aw.zz = fma(dz, vz, aw.zz);
+            }
+        }
+    AZP_D void body(const KernelArgs<S>&, const Head& h)
+        {
+        const S rsq = fma(h.dz, h.dz, fma(h.dy, h.dy, h.dx * h.dx));
+        one<EA>(types, rsq, h.tj, h.dx, h.dy, h.dz, fx, fy, fz, pe, w);
+        one<EB>(types_b, rsq, h.tj, h.dx, h.dy, h.dz, gx, gy, gz, qe, w_b);
+        }
+
+    AZP_D void reset()
+        {
+        fx = fy = fz = pe = S(0);
+        gx = gy = gz = qe = S(0);
+        w = Virial6<S>();
+        w_b = Virial6<S>();
+        }
+
+    AZP_D void finish(const KernelArgs<S>& a, unsigned int row, bool writer, unsigned int tpp)
+        {
+        for (unsigned int o = tpp >> 1; o > 0; o >>= 1)
+            {
+            fx += shfl_xor(fx, o);
+            fy += shfl_xor(fy, o);
+            fz += shfl_xor(fz, o);
+            pe += shfl_xor(pe, o);
+            gx += shfl_xor(gx, o);
+            gy += shfl_xor(gy, o);
+            gz += shfl_xor(gz, o);
+            qe += shfl_xor(qe, o);
+            if (VIRIAL)
+                {
+                w.reduce(o);
+                w_b.reduce(o);
+                }
+            }
+        if (writer)
+            {
+            store4(a.force, row, fx, fy, fz, S(0.5) * pe);
+            store4(a.force_b, row, gx, gy, gz, S(0.5) * qe);
+            if (VIRIAL)
+                {
+                w.store(a.virial, a.virial_pitch, row);
+                w_b.store(a.virial_b, a.virial_pitch, row);
+                }
+            }
+        }
+    };
+
+// =============================================================================================
 // DPD thermostat family: also gathers vel_j and tag_j; force from force_divr (conservative +
 // drag + random), virial from the conservative part only.
 // =============================================================================================
@@ -590,7 +769,14 @@ template<class E_, class S_, bool VIRIAL, int NTM_> struct DpdFamily
         // the scan's rsq is accumulated with FMAs; the decisive test (heavy) uses the
         // reference's rounding of rsq, so the scan admits a margin of a few ulp
         if (rsq < types.rcutsq_scaled(tj, S(1.0) + S(8) * (sizeof(S) == 4 ? S(1.1920929e-7) : S(2.220446049250313e-16))))
+            {
             queue.push(j);
+#ifdef AZP_DPD_PREFETCH
+            // the heavy round gathers vel[j] and tag[j] behind the pop: start them now (no register)
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(a.vel + 4 * (size_t)j));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(a.tag + j));
+#endif
+            }
         }
 
     // heavy part, one queued neighbour per lane (lanes with an empty queue idle)
@@ -659,23 +845,28 @@ template<class E_, class S_, bool VIRIAL, int NTM_> struct AnisoFamily
     // measured on C5 (51 % of the entries accepted, 16.6 per row): deferring the accepted pairs
     // (AcceptQueue) saves 11 % of the instructions but lengthens the dependent memory chains and
     // is 6 % slower, so the two-patch Morse family evaluates in place
-    static constexpr bool QUEUE = false;
+#ifndef AZP_ANISO_QUEUE
+#define AZP_ANISO_QUEUE 0
+#endif
+    static constexpr bool QUEUE = AZP_ANISO_QUEUE != 0;
 
     TypeLookup<E, S, NTM> types;
+    AcceptQueue queue;
     Vec4<S> qi;
     S fx = S(0), fy = S(0), fz = S(0), pe = S(0);
     S tx = S(0), ty = S(0), tz = S(0);
     Virial6<S> w;
 
-    AZP_HD static size_t smem_bytes(size_t ntp, size_t)
+    AZP_HD static size_t smem_bytes(size_t ntp, size_t block)
         {
-        return PairTable<E, S>::bytes(ntp) + 16;
+        return PairTable<E, S>::bytes(ntp) + 16 + (QUEUE ? AcceptQueue::bytes(block) : 0);
         }
 
     AZP_D void stage(const KernelArgs<S>& a, const typename E::param_type* params, unsigned int ntp)
         {
         PairTable<E, S>& tab = types.tab;
         tab.carve(ntp);
+        queue.carve(tab.end_off(ntp));
         for (unsigned int t = threadIdx.x; t < ntp; t += blockDim.x)
             {
             const S rc = a.rcutsq[t];
@@ -737,6 +928,30 @@ template<class E_, class S_, bool VIRIAL, int NTM_> struct AnisoFamily
             }
         }
 
+    // deferred-accept variant (AZP_ANISO_QUEUE): see AcceptQueue
+    AZP_D void scan(const KernelArgs<S>& a, const RowGeometry<S>& g, unsigned int j, const Vec4<S>& pj)
+        {
+        Vec3<S> dr;
+        g.displacement(a.box, pj, dr.x, dr.y, dr.z);
+        const S rsq = fma(dr.z, dr.z, fma(dr.y, dr.y, dr.x * dr.x));
+        const unsigned int tj = NTM == 1 ? 0u : scalar_as_uint(pj.w);
+        if (rsq <= types.rcutsq(tj))
+            {
+            queue.push(j);
+#ifdef AZP_ANISO_PREFETCH
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(a.orientation + 4 * (size_t)j));
+#endif
+            }
+        }
+    AZP_D void heavy(const KernelArgs<S>& a, const RowGeometry<S>& g)
+        {
+        if (queue.n > 0u)
+            {
+            const unsigned int j = queue.pop();
+            pair(a, g, j, load4(a.pos, j));
+            }
+        }
+
     AZP_D void reset()
         {
         fx = fy = fz = pe = S(0);
@@ -787,6 +1002,16 @@ AZP_D auto pair_dispatch(Fam&, const KernelArgs<S>&, const RowGeometry<S>&, unsi
 struct NoHead
     {
     };
+// a row is not streamed when its particle type has every partner switched off -- in BOTH
+// potentials for a fused family (detected by its BothOff tag)
+template<class Fam> AZP_D auto row_disabled_dispatch(const Fam& fam) -> decltype(typename Fam::BothOff(), bool())
+    {
+    return fam.types.row_disabled() && fam.types_b.row_disabled();
+    }
+template<class Fam, class... X> AZP_D bool row_disabled_dispatch(const Fam& fam, X...)
+    {
+    return fam.types.row_disabled();
+    }
 template<class Fam, class S>
 AZP_D auto head_dispatch(Fam& fam, const KernelArgs<S>& a, const RowGeometry<S>& g, unsigned int j, const Vec4<S>& pj)
     -> typename std::enable_if<Fam::PIPE == 2, typename Fam::Head>::type
@@ -875,7 +1100,7 @@ AZP_D void process_row(Fam& fam,
         g.skip_wrap = (a.box.flags == 2) && __all_sync(0xffffffffu, inside || !active);
         }
     fam.begin_row(a, i, g.ti);
-    if (fam.types.row_disabled())
+    if (row_disabled_dispatch(fam))
         n = 0; // e.g. Hertz acting only between colloids: solvent rows just write zeros
 
     // ---- the row as aligned uint4 vectors of neighbour indices ------------------------------
@@ -1048,17 +1273,54 @@ __global__ void __launch_bounds__(max_block<typename Fam::S>())
     const unsigned int lane = gtid & (tpp - 1u);
     if (!LONGPASS)
         {
-        const unsigned int slot = gtid >> tpp_log2;
+        // A group of tpp lanes takes the rows slot, slot + G, slot + 2 G, ... (G = groups in the
+        // grid); the launch layer sizes the grid so that this is `rows_per_group` rows
+        // (launch.cuh, kRowsPerGroup). With more than one row per group the (n_neigh, head_list)
+        // pair of the next row is loaded, and the first 128-byte line of its neighbour list
+        // prefetched into L1, while the current row is evaluated: a short row (C4: 35 entries,
+        // C5: 20) is otherwise two dependent cold misses (head, then the list line) in front of a
+        // few hundred cycles of work.
         const unsigned int nslots = a.row_ids ? a.n_row_ids : a.N;
-        bool active = slot < nslots;
-        unsigned int row = 0, n = 0;
-        uint64_t head = 0;
-        if (active)
+        const unsigned int groups = (gridDim.x * blockDim.x) >> tpp_log2;
+        const unsigned int per_warp = 32u >> tpp_log2;
+        const unsigned int in_warp = (gtid & 31u) >> tpp_log2;
+        unsigned int s0 = (gtid >> 5) * per_warp;
+        // metadata of the next two rows: (n, head) of row k + 2 is requested while row k is
+        // evaluated, so the prefetch of row k + 1's list line never waits for its address
+        unsigned int row_1 = 0, n_1 = 0, row_2 = 0, n_2 = 0;
+        uint64_t head_1 = 0, head_2 = 0;
+        bool act_1 = false, act_2 = false;
+        auto fetch = [&](unsigned int slot0, unsigned int& row, unsigned int& n, uint64_t& head, bool& active)
             {
-            row = a.row_ids ? __ldg(a.row_ids + slot) : slot;
-            n = __ldg(a.n_neigh + row);
-            head = __ldg(a.head_list + row);
-            if (a.long_queue && n > a.long_threshold)
+            const unsigned int slot = slot0 + in_warp;
+            active = slot0 < nslots && slot < nslots;
+            row = 0, n = 0, head = 0;
+            if (active)
+                {
+                row = a.row_ids ? __ldg(a.row_ids + slot) : slot;
+                n = __ldg(a.n_neigh + row);
+                head = __ldg(a.head_list + row);
+                }
+            };
+        fetch(s0, row_1, n_1, head_1, act_1);
+        if (s0 + groups < nslots)
+            fetch(s0 + groups, row_2, n_2, head_2, act_2);
+        bool first = true;
+        for (; s0 < nslots; s0 += groups)
+            {
+            unsigned int row = row_1, n = n_1;
+            uint64_t head = head_1;
+            bool active = act_1;
+            row_1 = row_2, n_1 = n_2, head_1 = head_2, act_1 = act_2;
+            act_2 = false;
+            if (s0 + groups < nslots)
+                {
+                if (s0 + 2u * groups < nslots)
+                    fetch(s0 + 2u * groups, row_2, n_2, head_2, act_2);
+                if (act_1 && lane == 0)
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(a.nlist + head_1));
+                }
+            if (active && a.long_queue && n > a.long_threshold)
                 {
                 // every lane of the group takes the same decision: lane 0 reserves the slot and
                 // broadcasts the outcome through the group's shuffle
@@ -1076,8 +1338,11 @@ __global__ void __launch_bounds__(max_block<typename Fam::S>())
                     n = 0;
                     }
                 }
+            if (!first)
+                fam.reset();
+            first = false;
+            process_row(fam, a, ntp, row, n, head, active, lane, tpp);
             }
-        process_row(fam, a, ntp, row, n, head, active, lane, tpp);
         }
     else
         {

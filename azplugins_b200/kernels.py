@@ -74,6 +74,16 @@ def launch(family, evaluator, bits, args, d_params, stream=None):
     _lib.check(rc, "pair-force launch")
 
 
+def launch_fused(ev_a, args_a, d_params_a, ev_b, args_b, d_params_b, bits, stream=None):
+    """Two isotropic potentials over one sweep of the list (``azp_pair_forces_fused_*``)."""
+    if stream is None:
+        stream = torch.cuda.current_stream().cuda_stream
+    fn = getattr(_lib.lib, "azp_pair_forces_fused_f%d" % bits)
+    rc = fn(ev_a, ctypes.byref(args_a), d_params_a, ev_b, ctypes.byref(args_b), d_params_b,
+            ctypes.c_void_p(stream))
+    _lib.check(rc, "fused pair-force launch")
+
+
 def autotune(family, evaluator, bits, args, d_params, stream=None):
     """(block_size, threads_per_particle, ms) of the fastest launch shape for these arguments."""
     if stream is None:

@@ -433,3 +433,77 @@ class TwoPatchMorse(AnisotropicPair):
     _evaluator = _lib.EV_TWO_PATCH_MORSE
     _param_schema = {"M_d": float, "M_r": float, "r_eq": float, "omega": float,
                      "alpha": float, "repulsion": bool}
+
+
+class FusedPair:
+    """Two attached isotropic potentials on ONE neighbour list evaluated in one sweep of the list
+    (C ABI ``azp_pair_forces_fused_*``). The reference's documented case is
+    ``Colloid`` + ``Hertz`` (reference src/pair.py:66-76), which HOOMD runs as two force computes
+    that each stream the list. Each potential keeps its own parameters, cutoffs, mode (none /
+    shift) and read-outs; after :meth:`compute` both hold exactly what their own ``compute()``
+    would have produced."""
+
+    SUPPORTED = {(_lib.EV_COLLOID, _lib.EV_HERTZ)}
+
+    def __init__(self, a, b):
+        if (a._evaluator, b._evaluator) not in self.SUPPORTED:
+            if (b._evaluator, a._evaluator) in self.SUPPORTED:
+                a, b = b, a
+            else:
+                raise ValueError("no fused kernel for (%s, %s)" % (type(a).__name__, type(b).__name__))
+        if a.nlist is not b.nlist:
+            raise ValueError("fused potentials must share one neighbour list")
+        if "xplor" in (a.mode, b.mode):
+            raise ValueError("xplor potentials are evaluated separately")
+        self.a, self.b = a, b
+
+    @staticmethod
+    def can_fuse(a, b):
+        pair_ok = (a._evaluator, b._evaluator) in FusedPair.SUPPORTED or \
+            (b._evaluator, a._evaluator) in FusedPair.SUPPORTED
+        return (pair_ok and a.nlist is b.nlist and "xplor" not in (a.mode, b.mode)
+                and a._family == _lib.FAMILY_PAIR and b._family == _lib.FAMILY_PAIR)
+
+    @property
+    def kernel_parameters(self):
+        return self.a.kernel_parameters
+
+    @kernel_parameters.setter
+    def kernel_parameters(self, value):
+        self.a.kernel_parameters = value
+
+    def compute(self, timestep=None, compute_virial=True, row_ids=None, rows=None):
+        a, b = self.a, self.b
+        if a._state is None or a._state is not b._state:
+            raise RuntimeError("fused potentials must be attached to the same State")
+        args_a = a._args(timestep, compute_virial, row_ids, rows)
+        args_b = b._args(timestep, compute_virial, row_ids, rows)
+        if args_a.N == 0:
+            return self
+        with torch.cuda.device(a._state.device):
+            kernels.launch_fused(a._evaluator, args_a, a._d_params.data_ptr(), b._evaluator, args_b,
+                                 b._d_params.data_ptr(), a._bits)
+        if row_ids is None and rows is None:
+            ts = a._state.timestep if timestep is None else int(timestep)
+            a._computed_at = (ts, a._tables_version)
+            b._computed_at = (ts, b._tables_version)
+        return self
+
+    def tune_kernel_parameters(self, timestep=None, compute_virial=True, reps=3):
+        """Scan (block_size, threads_per_particle) for the fused launch and pin the fastest."""
+        best = None
+        for block in (64, 128, 256):
+            for tpp in (1, 2, 4, 8):
+                self.kernel_parameters = (block, tpp)
+                self.compute(timestep, compute_virial)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(reps):
+                    self.compute(timestep, compute_virial)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / reps
+                if best is None or ms < best[2]:
+                    best = (block, tpp, ms)
+        self.kernel_parameters = best[:2]
+        return best

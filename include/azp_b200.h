@@ -156,6 +156,23 @@ int azp_aniso_forces_f32(int evaluator, const azp_pair_args* args, const void* d
 int azp_aniso_forces_f64(int evaluator, const azp_pair_args* args, const void* d_params,
                          const void* d_shape_params, void* stream);
 
+/* Fused two-potential pass: two isotropic potentials evaluated over ONE
+ * sweep of the neighbour list -- the reference's documented case is pair.Colloid + pair.Hertz on
+ * one nlist (src/pair.py:66-76), which HOOMD runs as two ForceComputes that each stream the
+ * list. `a` and `b` are the argument structs the two separate calls would get: they must name
+ * the same particles, rows and list (d_pos, d_n_neigh, d_nlist, d_head_list, N, ntypes,
+ * row_offset, d_row_ids, compute_virial, virial_pitch equal); outputs, d_rcutsq, shift_mode
+ * (none / shift) and parameters are per potential; launch parameters are taken from `a`. The
+ * outputs equal those of the two separate calls bit for bit. Supported pair: (AZP_EV_COLLOID,
+ * AZP_EV_HERTZ); anything else, or xplor, returns cudaErrorNotSupported (801) and the caller
+ * launches the potentials separately. */
+int azp_pair_forces_fused_f32(int evaluator_a, const azp_pair_args* a, const void* d_params_a,
+                              int evaluator_b, const azp_pair_args* b, const void* d_params_b,
+                              void* stream);
+int azp_pair_forces_fused_f64(int evaluator_a, const azp_pair_args* a, const void* d_params_a,
+                              int evaluator_b, const azp_pair_args* b, const void* d_params_b,
+                              void* stream);
+
 /* Launch autotuner (HOOMD Autotuner<2> equivalent): times the (block_size, threads_per_particle)
  * candidates on the given arguments with CUDA events, writes the fastest pair and its time.
  * family: 0 pair, 1 dpd, 2 aniso. Synchronises the stream. */
