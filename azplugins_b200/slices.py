@@ -188,19 +188,22 @@ class PeerHalo:
     The exchanged arrays live in symmetric memory (``torch.distributed._symmetric_memory``: the
     same allocation on every rank, peer-mapped). One kernel of the library (``azp_push_rows``)
     stores the particles a peer needs straight into that peer's ghost region -- consecutive
-    16-byte stores per peer, fire-and-forget over NVLink -- bracketed by two device-side
-    barriers on the symmetric-memory signal pads:
+    16-byte stores per peer, fire-and-forget over NVLink -- followed by ONE device-side barrier
+    on the symmetric-memory signal pads:
 
-        barrier   every rank has finished reading its ghosts (its previous force kernel precedes
-                  the barrier in stream order), so they may be overwritten
-        push      my particles -> the peers' ghost regions
-        barrier   every push has landed; the force kernel may read the ghosts
+        push      my particles -> the peers' ghost regions of buffer set p = step % 2
+        barrier   every push has landed; the force kernel may read the ghosts of set p
 
-    No pack buffer, no second stream, no interior/boundary split: the rows run in one launch in
-    natural order right after the second barrier.
+    The arrays are double-buffered: step t pushes into and computes from set t % 2. A peer last
+    read its set t % 2 in the force kernel of step t - 2, which precedes its barrier of step
+    t - 1 in stream order -- and this rank passed that barrier before it pushes -- so no second
+    barrier is needed to protect the ghosts that are overwritten (round 1 used two barriers per
+    step on a single set: 6.6 us each plus the skew they expose). No pack buffer, no second
+    stream, no interior/boundary split: the rows run in one launch in natural order right after
+    the barrier.
     """
 
-    def __init__(self, plan, arrays, group=None):
+    def __init__(self, plan, arrays, group=None, double_buffer=True):
         import torch.distributed._symmetric_memory as symm_mem
 
         self.plan = plan
@@ -211,36 +214,54 @@ class PeerHalo:
         n_rows = torch.tensor([arrays[0].shape[0]], dtype=torch.int64, device=dev)
         dist.all_reduce(n_rows, op=dist.ReduceOp.MAX, group=self.group)
         max_rows = int(n_rows.item())
-        self.arrays, self.handles, self.dst_addr = [], [], []
         self._send_cat = torch.cat([plan.send_idx[r] for r in self.peers]) if self.peers else None
-        for a in arrays:
-            sym = symm_mem.empty((max_rows, a.shape[1]), dtype=a.dtype, device=dev)
-            sym[:a.shape[0]].copy_(a)
-            hdl = symm_mem.rendezvous(sym, self.group)
-            row_bytes = a.shape[1] * a.element_size()
-            addr = []
-            for r in self.peers:
-                start = int(plan.peer_ghost_start[r][me])
-                base = int(hdl.buffer_ptrs[r]) + start * row_bytes
-                addr.append(base + row_bytes * torch.arange(int(plan.send_counts[r]), dtype=torch.int64))
-            self.arrays.append(sym[:a.shape[0]])
-            self.handles.append(hdl)
-            self.dst_addr.append(torch.cat(addr).to(dev) if addr else None)
+        self.sets = []  # per buffer set: (arrays, handles, dst_addr)
+        for _ in range(2 if double_buffer else 1):
+            sym_arrays, handles, dst_addr = [], [], []
+            for a in arrays:
+                sym = symm_mem.empty((max_rows, a.shape[1]), dtype=a.dtype, device=dev)
+                sym[:a.shape[0]].copy_(a)
+                hdl = symm_mem.rendezvous(sym, self.group)
+                row_bytes = a.shape[1] * a.element_size()
+                addr = []
+                for r in self.peers:
+                    start = int(plan.peer_ghost_start[r][me])
+                    base = int(hdl.buffer_ptrs[r]) + start * row_bytes
+                    addr.append(base + row_bytes * torch.arange(int(plan.send_counts[r]), dtype=torch.int64))
+                sym_arrays.append(sym[:a.shape[0]])
+                handles.append(hdl)
+                dst_addr.append(torch.cat(addr).to(dev) if addr else None)
+            self.sets.append((sym_arrays, handles, dst_addr))
+        self.parity = 0
+        self.barriers_per_step = 1 if double_buffer else 2
+
+    @property
+    def arrays(self):
+        """The buffer set the next force evaluation reads."""
+        return self.sets[self.parity][0]
 
     def bytes_per_step(self):
         n = int(sum(self.plan.recv_counts[r] for r in range(self.plan.world) if r != self.plan.rank))
         return sum(n * a.shape[1] * a.element_size() for a in self.arrays)
 
+    def advance(self):
+        """Switch to the other buffer set (call before filling this step's local particles)."""
+        if len(self.sets) == 2:
+            self.parity ^= 1
+        return self.arrays
+
     def __call__(self):
-        """Enqueue barrier, push, barrier on the current stream."""
+        """Enqueue push + barrier for the current buffer set on the current stream."""
         from . import kernels
 
-        h = self.handles[0]
-        h.barrier(channel=0)
+        arrays, handles, dst_addr = self.sets[self.parity]
+        h = handles[0]
+        if len(self.sets) == 1:
+            h.barrier(channel=0)  # single set: the readers of the ghosts must be done first
         if self.peers:
-            for a, dst in zip(self.arrays, self.dst_addr):
+            for a, dst in zip(arrays, dst_addr):
                 kernels.push_rows(a, self._send_cat, dst)
-        h.barrier(channel=1)
+        h.barrier(channel=1 + self.parity)
 
 
 class SliceScheduler:
@@ -271,11 +292,12 @@ class SliceScheduler:
                 self.peer_halo = None
                 self.transport = transport = "nccl"
         if self.peer_halo is not None:
-            for name in ("pos", "vel", "orientation"):
-                for old, new in zip(exchange_arrays, self.peer_halo.arrays):
+            self._exchanged_names = []
+            for old in exchange_arrays:
+                for name in ("pos", "vel", "orientation"):
                     if getattr(state, name) is old:
-                        setattr(state, name, new)
-            self.exchange_arrays = list(self.peer_halo.arrays)
+                        self._exchanged_names.append(name)
+            self._bind_buffer_set()
         elif transport != "nccl":
             raise ValueError("transport must be 'nccl' or 'peer'")
         self.n_local = plan.n_local
@@ -293,22 +315,49 @@ class SliceScheduler:
                                                   + (1 if plan.boundary_rows.numel() else 0))
         self._host = None
 
+    def _bind_buffer_set(self):
+        """Point the State (what the force kernels read) at the current symmetric buffer set."""
+        arrays = self.peer_halo.arrays
+        for name, arr in zip(self._exchanged_names, arrays):
+            setattr(self.state, name, arr)
+        self.exchange_arrays = list(arrays)
+
     # ---- construction from a synthetic workload ------------------------------------------
     @classmethod
     def from_workload(cls, wl, rank, world, device, dtype=np.float32, buffer=0.4, group=None,
-                      transport="nccl"):
+                      transport="nccl", balance="neighbors"):
         """Every rank generates the same global workload (seeded), builds the rows of its slice
-        on its GPU, derives the plan and keeps only local + ghost particles."""
+        on its GPU, derives the plan and keeps only local + ghost particles.
+
+        ``balance``: "neighbors" (default) cuts the sorted particle array where the running sum
+        of n_neigh reaches equal shares (rows of C3 are skewed, 1,860 entries for
+        a colloid against ~100 for a solvent particle) -- every rank counts the rows of the whole
+        system once at setup for that; "count" cuts at equal particle counts."""
         from . import nlist as aznlist
         from .state import State
 
-        bounds = partition_bounds(wl.N, world)
-        lo, hi = int(bounds[rank]), int(bounds[rank + 1])
         g = wl.make_state(dtype=dtype, device=device)  # global arrays, setup only
         cell = aznlist.Cell(buffer=buffer)
         probe = wl.make_potentials(cell)  # registers the cutoffs with the list
-        cell.build(g, rows=(lo, hi))
-        plan = SlicePlan(rank, world, bounds, cell.n_neigh, cell.head_list, cell.nlist)
+        if balance == "neighbors" and world > 1:
+            cell.build(g)  # all rows: the same list on every rank
+            weights = cell.n_neigh[:wl.N].cpu().numpy().astype(np.float64)
+            bounds = partition_bounds_weighted(weights, world)
+            lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+            start = int(cell.head_list[lo].item())
+            end = int(cell.head_list[hi].item()) if hi < wl.N else int(cell.size)
+            n_neigh = cell.n_neigh[lo:hi].clone()
+            head_list = (cell.head_list[lo:hi] - start).clone()
+            nlist_rows = cell.nlist[start:end].clone()
+            n_max = cell.n_max
+        elif balance in ("count", "neighbors"):
+            bounds = partition_bounds(wl.N, world)
+            lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+            cell.build(g, rows=(lo, hi))
+            n_neigh, head_list, nlist_rows, n_max = cell.n_neigh, cell.head_list, cell.nlist, cell.n_max
+        else:
+            raise ValueError("balance must be 'neighbors' or 'count'")
+        plan = SlicePlan(rank, world, bounds, n_neigh, head_list, nlist_rows)
         plan.negotiate(group)
         ids = torch.cat([torch.arange(lo, hi, device=g.pos.device), plan.ghost_ids])
         state = State.__new__(State)
@@ -321,7 +370,7 @@ class SliceScheduler:
         state.tag = g.tag[ids].contiguous()
         local_list = aznlist.NeighborList.from_arrays(plan.n_neigh, plan.nlist_local,
                                                       plan.head_list, device=device, buffer=buffer)
-        del g, cell, probe
+        del g, cell, probe, n_neigh, head_list, nlist_rows
         torch.cuda.empty_cache()
         pots = wl.make_potentials(local_list)
         for p in pots:
@@ -346,7 +395,11 @@ class SliceScheduler:
     def step(self, compute_virial=False):
         p = self.plan
         if self.peer_halo is not None:
-            # barrier, push over NVLink, barrier, then every row in one launch per potential
+            # next buffer set, push over NVLink, one barrier, then every row in one launch per
+            # potential. (In an MD loop the integrator writes the new local positions into the
+            # set that advance() returns; here the particles do not move, both sets hold them.)
+            self.peer_halo.advance()
+            self._bind_buffer_set()
             self.peer_halo()
             for pot in self.pots:
                 pot.compute(compute_virial=compute_virial)
@@ -463,7 +516,8 @@ class SliceScheduler:
             self._host = dict(
                 pos=torch.empty((self.n_local, 4), dtype=st.pos.dtype).pin_memory(),
                 force=torch.empty_like(self.pots[0]._force, device="cpu").pin_memory(),
-                virial=torch.empty_like(self.pots[0]._virial, device="cpu").pin_memory())
+                virial=torch.empty_like(self.pots[0]._virial, device="cpu").pin_memory(),
+                torque=torch.empty_like(self.pots[0]._torque, device="cpu").pin_memory())
             self._host["pos"].copy_(st.pos[:self.n_local])
         return self._host
 
@@ -473,15 +527,24 @@ class SliceScheduler:
         d2h = h["force"].numel() * h["force"].element_size() * len(self.pots)
         if compute_virial:
             d2h += h["virial"].numel() * h["virial"].element_size() * len(self.pots)
+        d2h += sum(h["torque"].numel() * h["torque"].element_size() for p in self.pots if p.is_anisotropic)
         return h2d, d2h
 
     def e2e_step(self, compute_virial=False):
+        """One step through host buffers: this rank's positions from pinned host memory, the halo
+        exchange, and the per-particle results delivered to pinned host memory in row chunks
+        whose device-to-host copies overlap the evaluation of the next chunk
+        (``Pair.compute_to_host``)."""
         h = self._host_buffers(compute_virial)
+        if self.peer_halo is not None:
+            self.peer_halo.advance()
+            self._bind_buffer_set()
         self.state.pos[:self.n_local].copy_(h["pos"], non_blocking=True)
-        self._step_done.record()
-        self.step(compute_virial)
+        if self.peer_halo is not None:
+            self.peer_halo()
+        else:
+            self._step_done.record()
+            self.halo(self.exchange_arrays)
         for pot in self.pots:
-            h["force"].copy_(pot._force, non_blocking=True)
-            if compute_virial:
-                h["virial"].copy_(pot._virial, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+            pot.compute_to_host(h["force"], h["virial"] if compute_virial else None,
+                                h["torque"] if pot.is_anisotropic else None)

@@ -37,7 +37,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, weighted=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -51,7 +51,14 @@ def _worker(rank, world, port, out):
         L = wl.box.L
         r_cut, buf = 1.6, 0.4
         nn, nl, head = orc.build_nlist(pos, L, r_cut + buf)
-        bounds = slices.partition_bounds(wl.N, world)
+        if weighted:
+            # balance the sum of (skewed) row weights instead of the row count, as
+            # SliceScheduler.from_workload(balance="neighbors") does with n_neigh
+            w = nn.astype(np.float64) * np.where(np.arange(wl.N) < wl.N // 4, 4.0, 1.0)
+            bounds = slices.partition_bounds_weighted(w, world)
+            assert abs(int(bounds[1]) - wl.N // 2) > wl.N // 10
+        else:
+            bounds = slices.partition_bounds(wl.N, world)
         lo, hi = int(bounds[rank]), int(bounds[rank + 1])
         # rows of this slice with global indices (what the GPU builder returns for rows=(lo,hi))
         h0 = int(head[lo])
@@ -118,11 +125,12 @@ def _worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
-def test_two_rank_halo_exchange_and_row_parity():
+@pytest.mark.parametrize("weighted", [False, True], ids=["by-count", "by-weight"])
+def test_two_rank_halo_exchange_and_row_parity(weighted):
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, out, weighted)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:
