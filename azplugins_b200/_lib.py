@@ -72,6 +72,19 @@ class AzpMdArgs(ctypes.Structure):
     ]
 
 
+class AzpLangevinArgs(ctypes.Structure):
+    _fields_ = [
+        ("d_tag", ctypes.c_void_p),
+        ("d_gamma", ctypes.c_void_p),
+        ("ntypes", ctypes.c_uint32),
+        ("seed", ctypes.c_uint32),
+        ("timestep", ctypes.c_uint64),
+        ("kT", ctypes.c_double),
+        ("rng_id", ctypes.c_uint32),
+        ("noiseless", ctypes.c_uint32),
+    ]
+
+
 class AzpWallArgs(ctypes.Structure):
     _fields_ = [
         ("d_force", ctypes.c_void_p),
@@ -178,6 +191,8 @@ EXPORTED_SYMBOLS = (
     "azp_nve_step_one_f64",
     "azp_nve_step_two_f32",
     "azp_nve_step_two_f64",
+    "azp_langevin_step_two_f32",
+    "azp_langevin_step_two_f64",
     "azp_dpd_alpha",
     "azp_philox4x32_10",
     "azp_nlist_cell_dim",
@@ -251,6 +266,10 @@ def _load():
             fn = getattr(lib, name + sfx)
             fn.argtypes = [ctypes.POINTER(AzpMdArgs), vp]
             fn.restype = i32
+    for sfx in ("_f32", "_f64"):
+        fn = getattr(lib, "azp_langevin_step_two" + sfx)
+        fn.argtypes = [ctypes.POINTER(AzpMdArgs), ctypes.POINTER(AzpLangevinArgs), vp]
+        fn.restype = i32
     lib.azp_dpd_alpha.argtypes = [i32, u32, u32, u32, ctypes.c_uint64]
     lib.azp_dpd_alpha.restype = ctypes.c_double
     lib.azp_philox4x32_10.argtypes = [vp, vp, vp]

@@ -174,6 +174,19 @@ template<class E, class S, class V3, class V4> class ContractAnisoEvaluator
           m_rcutsq(rcutsq), m_c(c)
         {
         }
+    // kernel hook (see eval_morse.cuh): a contract evaluator keeps the quaternion of particle i
+    typedef Vec4<S> row_type;
+    AZP_D static row_type make_row(const Vec4<S>& quat_i)
+        {
+        return quat_i;
+        }
+    struct FromRow
+        {
+        };
+    AZP_D ContractAnisoEvaluator(FromRow, const Vec3<S>& dr, const row_type& qi, const Vec4<S>& qj, S rcutsq, const cache_type& c)
+        : ContractAnisoEvaluator(dr, qi, qj, rcutsq, c)
+        {
+        }
     AZP_HD static bool disabled(const cache_type&)
         {
         return false;

@@ -93,7 +93,27 @@ template<class S> class AnisoPairEvaluatorTwoPatchMorse
                                           const Vec4<S>& _quat_j,
                                           S _rcutsq,
                                           const cache_type& _c)
-        : dr(_dr), rcutsq(_rcutsq), quat_i(_quat_i), quat_j(_quat_j), c(_c)
+        : dr(_dr), rcutsq(_rcutsq), ni(patch_director(_quat_i)), quat_j(_quat_j), c(_c)
+        {
+        }
+
+    // Kernel hook: what the evaluator needs of particle i's orientation, computed once per row
+    // (the patch director; the kernels keep it in registers instead of the quaternion).
+    typedef Vec3<S> row_type;
+    AZP_D static row_type make_row(const Vec4<S>& quat_i)
+        {
+        return patch_director(quat_i);
+        }
+    struct FromRow
+        {
+        };
+    AZP_D AnisoPairEvaluatorTwoPatchMorse(FromRow,
+                                          const Vec3<S>& _dr,
+                                          const row_type& _ni,
+                                          const Vec4<S>& _quat_j,
+                                          S _rcutsq,
+                                          const cache_type& _c)
+        : dr(_dr), rcutsq(_rcutsq), ni(_ni), quat_j(_quat_j), c(_c)
         {
         }
 
@@ -150,7 +170,6 @@ template<class S> class AnisoPairEvaluatorTwoPatchMorse
         S r, rinv;
         ref::r_and_rinv(ref::dot3(dr.x, dr.y, dr.z, dr.x, dr.y, dr.z), r, rinv);
         const Vec3<S> u {ref::mul(dr.x, rinv), ref::mul(dr.y, rinv), ref::mul(dr.z, rinv)};
-        const Vec3<S> ni = patch_director(quat_i);
         const Vec3<S> nj = patch_director(quat_j);
 
         S UM = -c.M_d;
@@ -229,7 +248,8 @@ template<class S> class AnisoPairEvaluatorTwoPatchMorse
     private:
     Vec3<S> dr;
     S rcutsq;
-    Vec4<S> quat_i, quat_j;
+    Vec3<S> ni;
+    Vec4<S> quat_j;
     const cache_type& c;
     };
     } // namespace azp

@@ -18,9 +18,6 @@ namespace azp
 // ---- long-row deferral scratch: one small queue per (device, stream), allocated on first use --
 constexpr unsigned int kLongRowThreshold = 512; // rows longer than this go to the second pass
 constexpr unsigned int kLongRowCapacity = 1u << 16;
-#ifndef AZP_ROWS_PER_GROUP
-#define AZP_ROWS_PER_GROUP 1
-#endif
 constexpr unsigned int kRowsPerGroup = AZP_ROWS_PER_GROUP;
 constexpr double kShortRow = 64.0; // mean row capacity up to which rows count as short
 struct LongRowScratch
@@ -102,7 +99,7 @@ inline bool is_pow2(unsigned int x)
 
 // Launch parameters: honour the caller's (block_size, threads_per_particle) -- HOOMD's autotuner
 // dimensions -- or choose them from the mean row capacity and the number of rows.
-inline cudaError_t choose_shape(const azp_pair_args& a, LaunchShape& s, unsigned int block_limit)
+inline cudaError_t choose_shape(const azp_pair_args& a, LaunchShape& s, unsigned int block_limit, bool multirow = false)
     {
     unsigned int block = a.block_size ? a.block_size : 128u;
     if (block % 32u != 0 || block > block_limit)
@@ -135,7 +132,7 @@ inline cudaError_t choose_shape(const azp_pair_args& a, LaunchShape& s, unsigned
     // the next row's metadata and list line prefetched -- never fewer CTAs than fill the machine
     unsigned long long grid = (threads + block - 1) / block;
     const double mean_cap_rows = a.size_neigh_list && a.N ? double(a.size_neigh_list) / a.N : 1e9;
-    if (kRowsPerGroup > 1 && mean_cap_rows <= kShortRow)
+    if (multirow && kRowsPerGroup > 1 && mean_cap_rows <= kShortRow)
         {
         const unsigned long long g = (grid + kRowsPerGroup - 1) / kRowsPerGroup;
         grid = g > 148ull * 16ull ? g : (grid < 148ull * 16ull ? grid : 148ull * 16ull);
@@ -321,7 +318,7 @@ template<class E, class S> cudaError_t launch_dpd(const azp_pair_args* a, const 
     if (!a->d_vel || !a->d_tag)
         return cudaErrorInvalidValue;
     LaunchShape s;
-    err = choose_shape(*a, s, max_block<S>());
+    err = choose_shape(*a, s, max_block<S>(), kRowsPerGroup > 1);
     if (err != cudaSuccess)
         return err;
     const KernelArgs<S> k = convert_args<S>(*a);
@@ -360,7 +357,7 @@ template<class E, class S> cudaError_t launch_aniso(const azp_pair_args* a, cons
     if (!a->d_orientation || !a->d_torque)
         return cudaErrorInvalidValue;
     LaunchShape s;
-    err = choose_shape(*a, s, max_block<S>());
+    err = choose_shape(*a, s, max_block<S>(), kRowsPerGroup > 1);
     if (err != cudaSuccess)
         return err;
     const KernelArgs<S> k = convert_args<S>(*a);

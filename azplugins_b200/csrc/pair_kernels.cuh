@@ -36,6 +36,16 @@
 
 #include <type_traits>
 
+// rows per group of lanes in the main pass of the short-row families (DPD, anisotropic); 1 = one
+// row per group (default: measured, the multi-row walk with next-row prefetch gains 2-4 % on
+// C4/C5 but its loop state costs every kernel 20-30 registers when compiled in)
+#ifndef AZP_ROWS_PER_GROUP
+#define AZP_ROWS_PER_GROUP 1
+#endif
+#ifndef AZP_TRIP_WRAP
+#define AZP_TRIP_WRAP 0
+#endif
+
 namespace azp
     {
 template<class S> struct KernelArgs
@@ -116,12 +126,23 @@ template<class S> struct RowGeometry
         dy = pi.y - pj.y;
         dz = pi.z - pj.z;
         if (!skip_wrap)
-            {
-            if (b.flags == 2)
-                min_image_ortho(Lx, Ly, Lz, ix, iy, iz, dx, dy, dz);
-            else
-                min_image_general(b, dx, dy, dz);
-            }
+            wrap(b, dx, dy, dz);
+        }
+    AZP_D void wrap(const BoxDim<S>& b, S& dx, S& dy, S& dz) const
+        {
+        if (b.flags == 2)
+            min_image_ortho(Lx, Ly, Lz, ix, iy, iz, dx, dy, dz);
+        else
+            min_image_general(b, dx, dy, dz);
+        }
+    // the same with the skip_wrap decision taken by the caller (once per trip of four neighbours)
+    template<bool WRAP> AZP_D void displacement_t(const BoxDim<S>& b, const Vec4<S>& pj, S& dx, S& dy, S& dz) const
+        {
+        dx = pi.x - pj.x;
+        dy = pi.y - pj.y;
+        dz = pi.z - pj.z;
+        if (WRAP)
+            wrap(b, dx, dy, dz);
         }
     };
 
@@ -364,6 +385,7 @@ template<class E_, class S_, bool XPLOR, bool VIRIAL, int NTM_> struct IsoFamily
     static constexpr int NTM = NTM_;
     static constexpr int PIPE = IsoTraits<E>::pipe;
     static constexpr bool QUEUE = false;
+    static constexpr bool MULTIROW = false;
 
     TypeLookup<E, S, NTM> types;
     unsigned int xplor_off;
@@ -425,6 +447,13 @@ template<class E_, class S_, bool XPLOR, bool VIRIAL, int NTM_> struct IsoFamily
         {
         Head h;
         g.displacement(a.box, pj, h.dx, h.dy, h.dz);
+        h.tj = NTM == 1 ? 0u : scalar_as_uint(pj.w);
+        return h;
+        }
+    template<bool WRAP> AZP_D Head head_t(const KernelArgs<S>& a, const RowGeometry<S>& g, const Vec4<S>& pj) const
+        {
+        Head h;
+        g.template displacement_t<WRAP>(a.box, pj, h.dx, h.dy, h.dz);
         h.tj = NTM == 1 ? 0u : scalar_as_uint(pj.w);
         return h;
         }
@@ -538,6 +567,7 @@ template<class EA, class EB, class S_, bool VIRIAL, int NTM_> struct FusedIsoFam
     static constexpr int NTM = NTM_;
     static constexpr int PIPE = 2;
     static constexpr bool QUEUE = false;
+    static constexpr bool MULTIROW = false;
 
     TypeLookup<EA, S, NTM> types; // potential A (row_kernel reads rc_max through it: see stage)
     TypeLookup<EB, S, NTM> types_b;
@@ -598,6 +628,13 @@ template<class EA, class EB, class S_, bool VIRIAL, int NTM_> struct FusedIsoFam
         {
         Head h;
         g.displacement(a.box, pj, h.dx, h.dy, h.dz);
+        h.tj = NTM == 1 ? 0u : scalar_as_uint(pj.w);
+        return h;
+        }
+    template<bool WRAP> AZP_D Head head_t(const KernelArgs<S>& a, const RowGeometry<S>& g, const Vec4<S>& pj) const
+        {
+        Head h;
+        g.template displacement_t<WRAP>(a.box, pj, h.dx, h.dy, h.dz);
         h.tj = NTM == 1 ? 0u : scalar_as_uint(pj.w);
         return h;
         }
@@ -691,6 +728,7 @@ template<class E_, class S_, bool VIRIAL, int NTM_> struct DpdFamily
     static constexpr int NTM = NTM_;
     static constexpr int PIPE = 0;
     static constexpr bool QUEUE = true;
+    static constexpr bool MULTIROW = AZP_ROWS_PER_GROUP > 1;
 
     TypeLookup<E, S, NTM> types;
     AcceptQueue queue;
@@ -729,12 +767,8 @@ template<class E_, class S_, bool VIRIAL, int NTM_> struct DpdFamily
         }
 
     template<class C>
-    AZP_D void accept(const KernelArgs<S>& a, const C& c, unsigned int j, S rsq, S rcutsq, S dx, S dy, S dz)
+    AZP_D void accept(const KernelArgs<S>& a, const C& c, const Vec4<S>& vj, unsigned int tag_j, S rsq, S rcutsq, S dx, S dy, S dz)
         {
-        // velocity and tag are only needed for accepted pairs (about a third of the list at
-        // buffer 0.4), so they are gathered behind the cutoff test
-        const Vec4<S> vj = load4(a.vel, j);
-        const unsigned int tag_j = __ldg(a.tag + j);
         const S rdotv = dx * (vi.x - vj.x) + dy * (vi.y - vj.y) + dz * (vi.z - vj.z);
         S force_divr = S(0), force_divr_cons = S(0), pair_eng = S(0);
         E eval(rsq, rcutsq, c);
@@ -784,8 +818,14 @@ template<class E_, class S_, bool VIRIAL, int NTM_> struct DpdFamily
         {
         if (queue.n > 0u)
             {
+            // velocity and tag are only needed for accepted pairs (about a third of the list at
+            // buffer 0.4), so they are gathered here, behind the scan's cutoff test -- together
+            // with the position, so that a round exposes one gather latency instead of two (the
+            // few entries inside the scan's ulp margin but outside the cutoff load them in vain)
             const unsigned int j = queue.pop();
             const Vec4<S> pj = load4(a.pos, j);
+            const Vec4<S> vj = load4(a.vel, j);
+            const unsigned int tag_j = __ldg(a.tag + j);
             S dx, dy, dz;
             g.displacement(a.box, pj, dx, dy, dz);
             // rsq = dot(dx, dx) rounded like the reference's host loop (no FMA): for s < 2 the
@@ -797,7 +837,7 @@ template<class E_, class S_, bool VIRIAL, int NTM_> struct DpdFamily
             if (rsq < rcutsq)
                 {
                 const Cache c = types.cache(tj);
-                accept(a, c, j, rsq, rcutsq, dx, dy, dz);
+                accept(a, c, vj, tag_j, rsq, rcutsq, dx, dy, dz);
                 }
             }
         }
@@ -849,10 +889,11 @@ template<class E_, class S_, bool VIRIAL, int NTM_> struct AnisoFamily
 #define AZP_ANISO_QUEUE 0
 #endif
     static constexpr bool QUEUE = AZP_ANISO_QUEUE != 0;
+    static constexpr bool MULTIROW = AZP_ROWS_PER_GROUP > 1;
 
     TypeLookup<E, S, NTM> types;
     AcceptQueue queue;
-    Vec4<S> qi;
+    typename E::row_type ri; // what the evaluator keeps of orientation_i (two-patch Morse: the director)
     S fx = S(0), fy = S(0), fz = S(0), pe = S(0);
     S tx = S(0), ty = S(0), tz = S(0);
     Virial6<S> w;
@@ -882,7 +923,7 @@ template<class E_, class S_, bool VIRIAL, int NTM_> struct AnisoFamily
     AZP_D void begin_row(const KernelArgs<S>& a, unsigned int i, unsigned int ti)
         {
         types.begin_row(ti, a.ntypes);
-        qi = load4(a.orientation, i);
+        ri = E::make_row(load4(a.orientation, i));
         }
 
     template<class C>
@@ -890,10 +931,13 @@ template<class E_, class S_, bool VIRIAL, int NTM_> struct AnisoFamily
         {
         // the orientation gather and the evaluator body are skipped for the (about half)
         // rejected entries
-        const Vec4<S> qj = load4(a.orientation, j);
+        accept(c, load4(a.orientation, j), rsq, rcutsq, dr);
+        }
+    template<class C> AZP_D void accept(const C& c, const Vec4<S>& qj, S rsq, S rcutsq, const Vec3<S>& dr)
+        {
         Vec3<S> force {S(0), S(0), S(0)}, torque_i {S(0), S(0), S(0)}, torque_j {S(0), S(0), S(0)};
         S pair_eng = S(0);
-        E eval(dr, qi, qj, rcutsq, c);
+        E eval(typename E::FromRow(), dr, ri, qj, rcutsq, c);
         eval.evaluatePair(rsq, force, pair_eng, false, torque_i, torque_j);
         fx += force.x;
         fy += force.y;
@@ -947,8 +991,16 @@ template<class E_, class S_, bool VIRIAL, int NTM_> struct AnisoFamily
         {
         if (queue.n > 0u)
             {
+            // both gathers of the round are issued together (one exposed latency, not two); the
+            // scan applied pair()'s own cutoff test to the same displacement, so it is not repeated
             const unsigned int j = queue.pop();
-            pair(a, g, j, load4(a.pos, j));
+            const Vec4<S> pj = load4(a.pos, j);
+            const Vec4<S> qj = load4(a.orientation, j);
+            Vec3<S> dr;
+            g.displacement(a.box, pj, dr.x, dr.y, dr.z);
+            const S rsq = fma(dr.z, dr.z, fma(dr.y, dr.y, dr.x * dr.x));
+            const unsigned int tj = NTM == 1 ? 0u : scalar_as_uint(pj.w);
+            accept(types.cache(tj), qj, rsq, types.rcutsq(tj), dr);
             }
         }
 
@@ -1023,6 +1075,20 @@ AZP_D auto head_dispatch(Fam&, const KernelArgs<S>&, const RowGeometry<S>&, unsi
     -> typename std::enable_if<Fam::PIPE != 2, NoHead>::type
     {
     return NoHead();
+    }
+template<bool WRAP, class Fam, class S, class H>
+AZP_D auto heads_dispatch(Fam& fam, const KernelArgs<S>& a, const RowGeometry<S>& g, const Vec4<S>& p0, const Vec4<S>& p1,
+                          const Vec4<S>& p2, const Vec4<S>& p3, H& h0, H& h1, H& h2, H& h3) -> typename std::enable_if<Fam::PIPE == 2>::type
+    {
+    h0 = fam.template head_t<WRAP>(a, g, p0);
+    h1 = fam.template head_t<WRAP>(a, g, p1);
+    h2 = fam.template head_t<WRAP>(a, g, p2);
+    h3 = fam.template head_t<WRAP>(a, g, p3);
+    }
+template<bool WRAP, class Fam, class S, class H>
+AZP_D auto heads_dispatch(Fam&, const KernelArgs<S>&, const RowGeometry<S>&, const Vec4<S>&, const Vec4<S>&, const Vec4<S>&,
+                          const Vec4<S>&, H&, H&, H&, H&) -> typename std::enable_if<Fam::PIPE != 2>::type
+    {
     }
 template<class Fam, class S, class H>
 AZP_D auto body_dispatch(Fam& fam, const KernelArgs<S>& a, const H& h) -> typename std::enable_if<Fam::PIPE == 2>::type
@@ -1143,10 +1209,19 @@ AZP_D void process_row(Fam& fam,
         while (v < v_end)
             {
             const unsigned int v1 = v + tpp, v2 = v1 + tpp;
+#if AZP_TRIP_WRAP
+            // one (warp-uniform) skip_wrap branch per trip instead of one per neighbour
+            decltype(head_dispatch(fam, a, g, 0u, p0)) h0, h1, h2, h3;
+            if (g.skip_wrap)
+                heads_dispatch<false>(fam, a, g, p0, p1, p2, p3, h0, h1, h2, h3);
+            else
+                heads_dispatch<true>(fam, a, g, p0, p1, p2, p3, h0, h1, h2, h3);
+#else
             const auto h0 = head_dispatch(fam, a, g, j_cur.x, p0);
             const auto h1 = head_dispatch(fam, a, g, j_cur.y, p1);
             const auto h2 = head_dispatch(fam, a, g, j_cur.z, p2);
             const auto h3 = head_dispatch(fam, a, g, j_cur.w, p3);
+#endif
             if (v1 < v_end)
                 {
                 j_cur = j_nxt;
@@ -1271,7 +1346,41 @@ __global__ void __launch_bounds__(max_block<typename Fam::S>())
     const unsigned int tpp = 1u << tpp_log2;
     const unsigned int gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned int lane = gtid & (tpp - 1u);
-    if (!LONGPASS)
+    if (!LONGPASS && !Fam::MULTIROW)
+        {
+        // one row per group of tpp lanes (the launch layer sizes the grid accordingly)
+        const unsigned int slot = gtid >> tpp_log2;
+        const unsigned int nslots = a.row_ids ? a.n_row_ids : a.N;
+        bool active = slot < nslots;
+        unsigned int row = 0, n = 0;
+        uint64_t head = 0;
+        if (active)
+            {
+            row = a.row_ids ? __ldg(a.row_ids + slot) : slot;
+            n = __ldg(a.n_neigh + row);
+            head = __ldg(a.head_list + row);
+            if (a.long_queue && n > a.long_threshold)
+                {
+                // every lane of the group takes the same decision: lane 0 reserves the slot and
+                // broadcasts the outcome through the group's shuffle
+                unsigned int pos = 0xffffffffu;
+                if (lane == 0)
+                    {
+                    pos = atomicAdd(a.long_count, 1u);
+                    if (pos < a.long_capacity)
+                        a.long_queue[pos] = row;
+                    }
+                pos = __shfl_sync(__activemask(), pos, 0, tpp);
+                if (pos < a.long_capacity)
+                    {
+                    active = false; // deferred: the second pass writes this row
+                    n = 0;
+                    }
+                }
+            }
+        process_row(fam, a, ntp, row, n, head, active, lane, tpp);
+        }
+    else if (!LONGPASS)
         {
         // A group of tpp lanes takes the rows slot, slot + G, slot + 2 G, ... (G = groups in the
         // grid); the launch layer sizes the grid so that this is `rows_per_group` rows

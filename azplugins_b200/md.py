@@ -20,13 +20,48 @@ class ConstantVolume:
     """``hoomd.md.methods.ConstantVolume(filter=All)`` without a thermostat: NVE."""
 
 
+class Langevin:
+    """``hoomd.md.methods.Langevin(filter=All, kT, default_gamma=1.0)``: velocity Verlet with the
+    drag ``-gamma v`` and a uniform random force of variance ``2 gamma kT / dt`` added in the second
+    half step (BASELINE.json configs[0] runs the PerturbedLennardJones fluid under it). ``gamma``
+    is a per-type dict (``langevin.gamma['A'] = 2.0``), types without an entry use
+    ``default_gamma``. The random numbers follow HOOMD's ``RandomGenerator(Seed(id, timestep,
+    seed), Counter(tag))`` (``azp_langevin_step_two_*``, include/azp_b200.h); HOOMD itself is not
+    in the reference tree, so the stream id (``rng_id``) is the recalled one and parity with
+    HOOMD's trajectory is unpinned -- the tests pin the restated arithmetic bit for bit and the
+    equilibrium temperature."""
+
+    RNG_ID = 24  # RNGIdentifier::TwoStepLangevin of HOOMD v7.0.1 as recalled
+
+    def __init__(self, kT, default_gamma=1.0, seed=0, filter=None, tally_reservoir_energy=False):
+        if filter is not None:
+            raise ValueError("only filter=All is supported")
+        self.kT = kT
+        self.default_gamma = float(default_gamma)
+        self.gamma = {}
+        self.seed = int(seed) & 0xFFFF
+        self.rng_id = self.RNG_ID
+        self.noiseless = False
+
+    def _kT_at(self, timestep):
+        return float(self.kT(timestep)) if callable(self.kT) else float(self.kT)
+
+    def _gamma_table(self, state):
+        import numpy as np
+
+        g = np.full(state.ntypes, self.default_gamma, dtype=state.dtype)
+        for name, value in self.gamma.items():
+            g[state.type_index(name) if isinstance(name, str) else int(name)] = value
+        return g
+
+
 class Integrator:
     def __init__(self, dt, forces=None, methods=None):
         self.dt = float(dt)
         self.forces = list(forces or [])
         self.methods = list(methods or [ConstantVolume()])
-        if len(self.methods) != 1 or not isinstance(self.methods[0], ConstantVolume):
-            raise ValueError("only one ConstantVolume (NVE) method is supported")
+        if len(self.methods) != 1 or not isinstance(self.methods[0], (ConstantVolume, Langevin)):
+            raise ValueError("one method: ConstantVolume (NVE) or Langevin")
         self._state = None
 
     def attach(self, state):
@@ -49,6 +84,17 @@ class Integrator:
             if f._state is not state:
                 f.attach(state)
         self._prepared = False
+        m = self.methods[0]
+        self._langevin = None
+        if isinstance(m, Langevin):
+            la = _lib.AzpLangevinArgs()
+            self._gamma = torch.from_numpy(m._gamma_table(state)).to(state.device)
+            la.d_tag = state.tag.data_ptr()
+            la.d_gamma = self._gamma.data_ptr()
+            la.ntypes = state.ntypes
+            la.seed = m.seed
+            la.rng_id = m.rng_id
+            self._langevin = la
         return self
 
     def _args(self):
@@ -89,7 +135,21 @@ class Integrator:
         self._call("azp_nve_step_one", args)
         self._state.timestep += 1
         self._compute_forces(compute_virial)
-        self._call("azp_nve_step_two", args)
+        self._step_two(args)
+
+    def _step_two(self, args):
+        la = self._langevin
+        if la is None:
+            return self._call("azp_nve_step_two", args)
+        st, m = self._state, self.methods[0]
+        la.timestep = st.timestep
+        la.kT = m._kT_at(st.timestep)
+        la.noiseless = 1 if m.noiseless else 0
+        bits = 8 * st.dtype.itemsize
+        with torch.cuda.device(st.device):
+            stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+            rc = getattr(_lib.lib, "azp_langevin_step_two_f%d" % bits)(ctypes.byref(args), ctypes.byref(la), stream)
+        _lib.check(rc, "azp_langevin_step_two")
 
     def run(self, steps, compute_virial=False, graph=False):
         """Advance ``steps`` time steps (``sim.run(steps)``).
@@ -115,6 +175,8 @@ class Integrator:
             for _ in range(steps):
                 self._one_step(a, compute_virial)
             return self
+        if self._langevin is not None:
+            raise ValueError("graph=True needs a method that does not depend on the time step (Langevin)")
         lists = self._graph_lists()
         done = 0
         g, g_builds = None, None

@@ -289,6 +289,30 @@ int azp_nve_step_one_f64(const azp_md_args* args, void* stream);
 int azp_nve_step_two_f32(const azp_md_args* args, void* stream);
 int azp_nve_step_two_f64(const azp_md_args* args, void* stream);
 
+/* Langevin thermostat (hoomd.md.methods.Langevin; BASELINE.json configs[0] runs the
+ * PerturbedLennardJones fluid under it). Step one is azp_nve_step_one; this step two adds the
+ * Brownian force per particle before the second half kick:
+ *   F_bd = coeff (r_x, r_y, r_z) - gamma v;  coeff = sqrt(6 gamma kT / dt);  r ~ Uniform(-1, 1)
+ *   a = (sum of d_forces + F_bd) / m;  v += a dt / 2
+ * gamma per particle type (type id bit-cast in pos.w; args->d_pos must be set). Random numbers:
+ * HOOMD's RandomGenerator(Seed(rng_id, timestep, seed), Counter(tag)), three draws (Philox4x32-10,
+ * SURVEY.md Appendix B). HOOMD is not in the reference tree: rng_id (24 = RNGIdentifier::
+ * TwoStepLangevin as recalled from HOOMD v7.0.1) is a caller-supplied field, parity with HOOMD's
+ * stream is unpinned. IEEE arithmetic without FMA contraction. */
+typedef struct azp_langevin_args
+    {
+    const uint32_t* d_tag; /* u32[N] */
+    const void* d_gamma;   /* Scalar[ntypes] */
+    uint32_t ntypes;
+    uint32_t seed;         /* 16 bits used */
+    uint64_t timestep;
+    double kT;
+    uint32_t rng_id;       /* 8 bits used */
+    uint32_t noiseless;    /* != 0: drag only (HOOMD's tally / noiseless_t) */
+    } azp_langevin_args;
+int azp_langevin_step_two_f32(const azp_md_args* args, const azp_langevin_args* langevin, void* stream);
+int azp_langevin_step_two_f64(const azp_md_args* args, const azp_langevin_args* langevin, void* stream);
+
 /* Uniform(-1,1) value the DPD evaluator draws for a pair (host side; same code as the kernel).
  * Exposes the RNG keying of src/DPDPairEvaluatorGeneralWeight.h:213-233 for parity tests. */
 double azp_dpd_alpha(int scalar_bits, uint32_t seed, uint32_t tag_i, uint32_t tag_j, uint64_t timestep);

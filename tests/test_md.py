@@ -178,3 +178,113 @@ def test_dpd_temperature_reference_test():
         assert avg == pytest.approx(1.5, 0.1)
         # momentum is conserved by the pairwise random and drag forces
         assert np.abs(ig.momentum()).max() < 1e-2 * np.sqrt(N * kT)
+
+
+def _philox_u32(ctr0, tags, key0, key1):
+    """First output word of Philox4x32-10 for counters {ctr0, 0, 0, tag} (numpy, uint64 maths)."""
+    M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+    mask = np.uint64(0xFFFFFFFF)
+    c = [np.full(tags.shape, ctr0, np.uint64), np.zeros(tags.shape, np.uint64),
+         np.zeros(tags.shape, np.uint64), tags.astype(np.uint64)]
+    k0, k1 = key0, key1
+    for _ in range(10):
+        p0 = np.uint64(M0) * c[0]
+        p1 = np.uint64(M1) * c[2]
+        c = [(p1 >> np.uint64(32)) ^ c[1] ^ np.uint64(k0), p1 & mask,
+             (p0 >> np.uint64(32)) ^ c[3] ^ np.uint64(k1), p0 & mask]
+        k0, k1 = (k0 + W0) & 0xFFFFFFFF, (k1 + W1) & 0xFFFFFFFF
+    return c[0].astype(np.uint64), c[1].astype(np.uint64)
+
+
+def _numpy_langevin_two(vel, forces, tags, gamma, kT, dt, seed, timestep, rng_id):
+    S = vel.dtype.type
+    F = np.zeros_like(forces[0])
+    for f in forces:
+        F = F + f
+    key0 = ((rng_id & 0xFF) << 24) | ((seed & 0xFFFF) << 8) | ((timestep >> 32) & 0xFF)
+    key1 = timestep & 0xFFFFFFFF
+    r = np.zeros((len(vel), 3), dtype=vel.dtype)
+    for d in range(3):
+        w0, w1 = _philox_u32(d, tags, key0, key1)
+        if vel.dtype == np.float32:
+            u = w0.astype(np.float32) * S(2.3283064365386963e-10) + S(1.1641532182693481e-10)
+        else:
+            u = ((w0 << np.uint64(32)) | w1).astype(np.float64) * S(5.421010862427522e-20) + S(2.710505431213761e-20)
+        r[:, d] = S(-1) + S(2) * u
+    coeff = np.sqrt(S(6) * gamma * S(kT) / S(dt))
+    bd = r * coeff[:, None] - gamma[:, None] * vel[:, :3]
+    minv = S(1.0) / vel[:, 3]
+    a = np.zeros_like(vel)
+    a[:, :3] = (F[:, :3] + bd) * minv[:, None]
+    v = vel.copy()
+    v[:, :3] = vel[:, :3] + a[:, :3] * (S(0.5) * S(dt))
+    return v, a, F
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_langevin_step_two_bit_exact_against_numpy(dtype):
+    """azp_langevin_step_two_*: drag + uniform random force keyed by (rng id, time step, seed, tag)
+    exactly as the numpy restatement (Philox4x32-10 in uint64 arithmetic), two particle types with
+    different gamma, a time step above 2^32."""
+    import azplugins_b200 as az
+
+    rng = np.random.default_rng(21)
+    N, L, dt, kT, seed = 30011, (9.0, 11.0, 13.0), 0.004, 1.3, 0xBEEF
+    xyz = rng.uniform(-0.49, 0.49, (N, 3)) * np.array(L)
+    typeid = rng.integers(0, 2, N)
+    state = az.State(az.Box(*L), ["A", "B"], xyz, typeid=typeid, velocity=rng.standard_normal((N, 3)),
+                     mass=rng.uniform(0.5, 2.0, N), dtype=dtype)
+    state.tag.copy_(torch.from_numpy(rng.permutation(N).astype(np.int32)).to(state.tag.dtype))
+    bar = az.external.SphericalHarmonicBarrier(location=3.0)
+    bar.params["A"] = dict(k=20.0, offset=0.0)
+    bar.params["B"] = dict(k=10.0, offset=0.1)
+    method = az.md.Langevin(kT=kT, default_gamma=1.5, seed=seed)
+    method.gamma["B"] = 0.25
+    ig = az.md.Integrator(dt=dt, forces=[bar], methods=[method]).attach(state)
+    state.timestep = (3 << 32) + 12345
+    bar.compute()
+    v0 = state.vel.cpu().numpy()
+    ig._step_two(ig._args())
+    gamma = np.where(typeid == 0, 1.5, 0.25).astype(dtype)
+    tags = state.tag.cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+    v1, a1, F = _numpy_langevin_two(v0, [bar._force.cpu().numpy()], tags, gamma, kT, dt, seed,
+                                    state.timestep, az.md.Langevin.RNG_ID)
+    assert np.array_equal(state.vel.cpu().numpy(), v1)
+    assert np.array_equal(ig.accel.cpu().numpy()[:, :3], a1[:, :3])
+    assert np.array_equal(ig.net_force.cpu().numpy(), F)
+    # noiseless: drag only
+    method.noiseless = True
+    state.vel.copy_(torch.from_numpy(v0))
+    ig._step_two(ig._args())
+    minv = dtype(1.0) / v0[:, 3]
+    a_drag = (F[:, :3] + (-gamma[:, None] * v0[:, :3])) * minv[:, None]
+    assert np.array_equal(ig.accel.cpu().numpy()[:, :3], a_drag)
+
+
+def test_langevin_config1_reaches_kT():
+    """BASELINE.json configs[0] in small: PerturbedLennardJones fluid (rho = 0.8, r_cut = 3) under
+    Langevin NVT. The kinetic temperature relaxes to kT from a cold start and stays there; the
+    random force of two steps differs, that of the same (step, seed) does not."""
+    import azplugins_b200 as az
+    from azplugins_b200 import synth
+
+    rng = np.random.default_rng(3)
+    N, kT = 8000, 1.2
+    xyz, L = synth.jittered_lattice(N, 0.8, rng, jitter=0.05)
+    state = az.State(az.Box.cube(L), ["A"], xyz, velocity=np.zeros((N, 3)), dtype=np.float32)
+    nl = az.nlist.Cell(buffer=0.4)
+    plj = az.pair.PerturbedLennardJones(nlist=nl, default_r_cut=3.0, mode="shift")
+    plj.params[("A", "A")] = dict(epsilon=1.0, sigma=1.0, attraction_scale_factor=0.5)
+    ig = az.md.Integrator(dt=0.005, forces=[plj], methods=[az.md.Langevin(kT=kT, default_gamma=1.0, seed=5)])
+    ig.attach(state)
+    ig.run(1500)  # ~7.5 relaxation times
+    samples = []
+    for _ in range(100):
+        ig.run(5)
+        samples.append(2.0 * ig.kinetic_energy() / (3 * N))
+    avg = float(np.mean(samples))
+    print("Langevin <kT> =", avg)
+    assert avg == pytest.approx(kT, rel=0.03)
+    assert nl.num_builds > 3
+    with pytest.raises(ValueError):
+        ig.run(2, graph=True)
