@@ -157,6 +157,10 @@ class AzpNlistArgs(ctypes.Structure):
         ("_pad", ctypes.c_uint32),
         ("d_capacity", ctypes.c_void_p),
         ("d_overflow", ctypes.c_void_p),
+        ("d_cell_pos", ctypes.c_void_p),
+        ("d_pos_at_build", ctypes.c_void_p),
+        ("threads_per_row", ctypes.c_uint32),
+        ("_pad2", ctypes.c_uint32),
     ]
 
 
@@ -193,6 +197,10 @@ EXPORTED_SYMBOLS = (
     "azp_nve_step_two_f64",
     "azp_langevin_step_two_f32",
     "azp_langevin_step_two_f64",
+    "azp_nlist_moved_f32",
+    "azp_nlist_moved_f64",
+    "azp_sfc_order_f32",
+    "azp_sfc_order_f64",
     "azp_dpd_alpha",
     "azp_philox4x32_10",
     "azp_nlist_cell_dim",
@@ -279,6 +287,13 @@ def _load():
                  "azp_nlist_count_f64", "azp_nlist_fill_f32", "azp_nlist_fill_f64"):
         getattr(lib, name).argtypes = [ctypes.POINTER(AzpNlistArgs), vp]
         getattr(lib, name).restype = i32
+    for sfx in ("_f32", "_f64"):
+        fn = getattr(lib, "azp_nlist_moved" + sfx)
+        fn.argtypes = [vp, vp, ctypes.POINTER(AzpBox), ctypes.c_double, u32, vp, vp]
+        fn.restype = i32
+        fn = getattr(lib, "azp_sfc_order" + sfx)
+        fn.argtypes = [vp, ctypes.POINTER(AzpBox), u32, vp, vp]
+        fn.restype = i32
     if lib.azp_abi_version() != 1:
         raise ImportError("azplugins_b200: ABI version mismatch in " + LIB_PATH)
     return lib

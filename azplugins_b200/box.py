@@ -23,6 +23,12 @@ class Box:
     def volume(self):
         return self.Lx * self.Ly * self.Lz
 
+    def nearest_plane_distance(self):
+        """Distances between opposite faces (``hoomd.Box``'s nearest plane distances): what bounds
+        the cutoff under the minimum-image convention in a tilted box."""
+        t = self.xy * self.yz - self.xz
+        return (self.Lx / (1.0 + self.xy ** 2 + t ** 2) ** 0.5, self.Ly / (1.0 + self.yz ** 2) ** 0.5, self.Lz)
+
     def to_c(self):
         b = _lib.AzpBox()
         for d, v in enumerate(self.L):

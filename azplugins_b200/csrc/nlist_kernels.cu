@@ -4,13 +4,16 @@
 // exactly the arrays the force kernels (and HOOMD's NeighborListGPU) use: n_neigh[i] valid
 // entries of row i starting at nlist[head_list[i]], every j != i with
 // |minImage(r_i - r_j)|^2 < r_list(type_i, type_j)^2, full storage.
-// Orthorhombic boxes; rows are ordered by stencil cell (z, y, x from -1 to +1) and by particle
-// index inside a cell, so the build is deterministic and, for spatially sorted particles,
-// consecutive entries of a row are consecutive indices (coalesced position gathers later).
+// Orthorhombic and triclinic boxes; rows are ordered by stencil cell (z, y, x from -1 to +1) and
+// by particle index inside a cell, so the build is deterministic and, for spatially sorted
+// particles, consecutive entries of a row are consecutive indices (coalesced position gathers
+// later). Also here: the device-side displacement check and the Morton (SFC) particle order.
 #include "../../include/azp_b200.h"
 #include "azp_core.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
+
+#include <cmath>
 
 namespace azp
     {
@@ -33,6 +36,8 @@ template<class S> struct NlistArgs
     unsigned int* cell_of;
     unsigned int* cell_start;
     unsigned int* cell_order;
+    S* cell_pos;     // positions in cell order (contiguous per cell)
+    S* pos_at_build; // optional copy of pos for the displacement check
     CellGrid grid;
     unsigned int row_offset;
     unsigned int n_rows;
@@ -40,15 +45,19 @@ template<class S> struct NlistArgs
     unsigned int* overflow;
     };
 
+// Cell of a position: fractional coordinates of the (possibly triclinic) box -- HOOMD's
+// BoxDim::makeFraction -- periodic axes wrapped, non-periodic axes clamped (a particle slightly
+// outside the box on a wall-confined axis stays in the boundary cell, next to its neighbours).
 template<class S> AZP_D void cell_coords(const BoxDim<S>& b, const CellGrid& g, S x, S y, S z, int c[3])
     {
-    const S p[3] = {x, y, z};
+    const S p[3] = {x - b.xy * y - (b.xz - b.xy * b.yz) * z, y - b.yz * z, z};
 #pragma unroll
     for (int d = 0; d < 3; ++d)
         {
         S f = p[d] * b.Linv[d] + S(0.5);
-        f -= floor(f);
-        int ci = (int)(f * S(g.dim[d]));
+        if (b.periodic[d])
+            f -= floor(f);
+        int ci = (int)floor(f * S(g.dim[d]));
         ci = max(0, min((int)g.dim[d] - 1, ci));
         c[d] = ci;
         }
@@ -64,6 +73,8 @@ template<class S> __global__ void nlist_assign_cells(const NlistArgs<S> a, unsig
     cell_coords(a.box, a.grid, p.x, p.y, p.z, c);
     a.cell_of[i] = ((unsigned int)c[2] * a.grid.dim[1] + (unsigned int)c[1]) * a.grid.dim[0] + (unsigned int)c[0];
     iota[i] = i;
+    if (a.pos_at_build)
+        store4(a.pos_at_build, i, p.x, p.y, p.z, p.w);
     }
 
 // cell_start[c] = first position in the sorted key array whose key is >= c (c = 0 .. ncells)
@@ -84,62 +95,131 @@ __global__ void nlist_cell_starts(const unsigned int* sorted_cells, unsigned int
     cell_start[c] = lo;
     }
 
-template<class S, bool FILL> __global__ void __launch_bounds__(128) nlist_rows(const NlistArgs<S> a)
+// cell_pos[s] = pos[cell_order[s]]: the candidates of a cell become one contiguous run of
+// 16-byte elements (a broadcast / coalesced load in the row kernel instead of index -> gather)
+template<class S> __global__ void nlist_sorted_positions(const NlistArgs<S> a)
     {
-    const unsigned int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= a.n_rows)
+    const unsigned int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= a.N)
         return;
-    const unsigned int i = r + a.row_offset;
+    const Vec4<S> p = load4(a.pos, a.cell_order[s]);
+    store4(a.cell_pos, s, p.x, p.y, p.z, p.w);
+    }
+
+// The rows. A group of TPP lanes owns a row; it walks the 27 stencil cells in a fixed order
+// (z, y, x from -1 to +1) and, inside a cell, the candidates in cell order (= particle index),
+// TPP at a time: one 16-byte load of the cell-sorted position, the displacement, the cutoff test
+// of the type pair, and an ordered append (ballot + prefix popcount inside the group), so the
+// entries of a row come out in the same deterministic order whatever TPP is.
+//
+// Minimum image without rint(): the periodic image of a candidate is fixed by how its stencil
+// cell was reached -- wrapped below 0 or above dim - 1 on an axis means image -1 / +1 on that
+// axis -- so the group applies BoxDim::minImage's own update sequence (z, then y, then x, with
+// the tilt factors) with that image number instead of rint(d / L). For every pair closer than
+// r_list (<= cell width <= L / 3) the two agree bit for bit; farther candidates fail the cutoff
+// either way. An axis with a single cell (box shorter than 3 r_list) keeps rint().
+template<class S, bool FILL, unsigned int TPP> __global__ void __launch_bounds__(128) nlist_rows(const NlistArgs<S> a)
+    {
+    const unsigned int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned int lane = gtid & (TPP - 1u);
+    const unsigned int r = gtid / TPP;
+    const bool active = r < a.n_rows;
+    const unsigned int i = active ? r + a.row_offset : 0u;
     const Vec4<S> pi = load4(a.pos, i);
-    const unsigned int ti = scalar_as_uint(pi.w);
+    const unsigned int ti = min(scalar_as_uint(pi.w), a.ntypes - 1u);
     int c[3];
     cell_coords(a.box, a.grid, pi.x, pi.y, pi.z, c);
     unsigned int count = 0;
-    unsigned int* row = FILL ? a.nlist + a.head_list[r] : nullptr;
-    const unsigned int cap = (FILL && a.capacity) ? a.capacity[r] : 0xffffffffu;
+    unsigned int* row = (FILL && active) ? a.nlist + a.head_list[r] : nullptr;
+    const unsigned int cap = (FILL && a.capacity && active) ? a.capacity[r] : 0xffffffffu;
+    const unsigned int group_shift = (threadIdx.x & 31u) & ~(TPP - 1u);
+    const unsigned int group_mask = TPP == 32u ? 0xffffffffu : ((1u << TPP) - 1u);
+    const int dx_ = (int)a.grid.dim[0], dy_ = (int)a.grid.dim[1], dz_ = (int)a.grid.dim[2];
+    const BoxDim<S>& b = a.box;
     for (int oz = -a.grid.reach[2]; oz <= a.grid.reach[2]; ++oz)
         for (int oy = -a.grid.reach[1]; oy <= a.grid.reach[1]; ++oy)
             for (int ox = -a.grid.reach[0]; ox <= a.grid.reach[0]; ++ox)
                 {
                 int cx = c[0] + ox, cy = c[1] + oy, cz = c[2] + oz;
-                const int dx_ = (int)a.grid.dim[0], dy_ = (int)a.grid.dim[1], dz_ = (int)a.grid.dim[2];
+                // image of the candidates of this cell relative to particle i (r_i - r_j is
+                // brought back by -img * L): reached by wrapping below 0 -> the candidates sit
+                // one box length above -> r_i - r_j is about -L -> img = -1
+                S imgx = S(0), imgy = S(0), imgz = S(0);
+                bool skip = !active;
                 if (cx < 0 || cx >= dx_)
                     {
-                    if (!a.box.periodic[0])
-                        continue;
-                    cx = (cx + dx_) % dx_;
+                    skip = skip || !b.periodic[0];
+                    imgx = cx < 0 ? S(-1) : S(1);
+                    cx = cx < 0 ? cx + dx_ : cx - dx_;
                     }
                 if (cy < 0 || cy >= dy_)
                     {
-                    if (!a.box.periodic[1])
-                        continue;
-                    cy = (cy + dy_) % dy_;
+                    skip = skip || !b.periodic[1];
+                    imgy = cy < 0 ? S(-1) : S(1);
+                    cy = cy < 0 ? cy + dy_ : cy - dy_;
                     }
                 if (cz < 0 || cz >= dz_)
                     {
-                    if (!a.box.periodic[2])
-                        continue;
-                    cz = (cz + dz_) % dz_;
+                    skip = skip || !b.periodic[2];
+                    imgz = cz < 0 ? S(-1) : S(1);
+                    cz = cz < 0 ? cz + dz_ : cz - dz_;
                     }
-                const unsigned int cell = ((unsigned int)cz * a.grid.dim[1] + (unsigned int)cy) * a.grid.dim[0] + (unsigned int)cx;
-                const unsigned int s0 = a.cell_start[cell], s1 = a.cell_start[cell + 1];
-                for (unsigned int s = s0; s < s1; ++s)
+                unsigned int s0 = 0, s1 = 0;
+                if (!skip)
                     {
-                    const unsigned int j = a.cell_order[s];
-                    if (j == i)
-                        continue;
-                    const Vec4<S> pj = load4(a.pos, j);
-                    S dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
-                    min_image_general(a.box, dx, dy, dz);
-                    const S rsq = dx * dx + dy * dy + dz * dz;
-                    if (rsq < a.rlistsq[index2d(a.ntypes, ti, scalar_as_uint(pj.w))])
+                    const unsigned int cell = ((unsigned int)cz * a.grid.dim[1] + (unsigned int)cy) * a.grid.dim[0] + (unsigned int)cx;
+                    s0 = a.cell_start[cell], s1 = a.cell_start[cell + 1];
+                    }
+                // warp-uniform trip count (the groups of a warp may look at different cells)
+                const unsigned int trips = __reduce_max_sync(0xffffffffu, (s1 - s0 + TPP - 1u) / TPP);
+                for (unsigned int k = 0; k < trips; ++k)
+                    {
+                    const unsigned int s = s0 + k * TPP + lane;
+                    bool pass = false;
+                    unsigned int j = 0;
+                    if (s < s1)
                         {
-                        if (FILL && count < cap)
-                            row[count] = j;
-                        ++count;
+                        const Vec4<S> pj = load4(a.cell_pos, s);
+                        S x = pi.x - pj.x, y = pi.y - pj.y, z = pi.z - pj.z;
+                        // BoxDim::minImage's sequence with the image numbers of this cell
+                        if (b.periodic[2])
+                            {
+                            const S img = a.grid.reach[2] ? imgz : rint_small(z * b.Linv[2]);
+                            z -= b.L[2] * img;
+                            y -= b.L[2] * b.yz * img;
+                            x -= b.L[2] * b.xz * img;
+                            }
+                        if (b.periodic[1])
+                            {
+                            const S img = a.grid.reach[1] ? imgy : rint_small(y * b.Linv[1]);
+                            y -= b.L[1] * img;
+                            x -= b.L[1] * b.xy * img;
+                            }
+                        if (b.periodic[0])
+                            {
+                            const S img = a.grid.reach[0] ? imgx : rint_small(x * b.Linv[0]);
+                            x -= b.L[0] * img;
+                            }
+                        const S rsq = x * x + y * y + z * z;
+                        const unsigned int tj = min(scalar_as_uint(pj.w), a.ntypes - 1u);
+                        if (rsq < a.rlistsq[index2d(a.ntypes, ti, tj)])
+                            {
+                            j = a.cell_order[s];
+                            pass = j != i;
+                            }
                         }
+                    const unsigned int votes = (__ballot_sync(0xffffffffu, pass) >> group_shift) & group_mask;
+                    if (pass)
+                        {
+                        const unsigned int slot = count + __popc(votes & ((1u << lane) - 1u));
+                        if (FILL && slot < cap)
+                            row[slot] = j;
+                        }
+                    count += __popc(votes);
                     }
                 }
+    if (!active || lane != 0)
+        return;
     if (!FILL)
         a.n_neigh[r] = count;
     else if (a.capacity)
@@ -152,22 +232,34 @@ template<class S, bool FILL> __global__ void __launch_bounds__(128) nlist_rows(c
         }
     }
 
+template<class S> static BoxDim<S> nlist_box(const azp_box& ab)
+    {
+    BoxDim<S> b;
+    for (int d = 0; d < 3; ++d)
+        {
+        b.L[d] = S(ab.L[d]);
+        b.Linv[d] = S(1.0) / b.L[d];
+        b.periodic[d] = ab.periodic[d];
+        }
+    b.xy = S(ab.tilt[0]);
+    b.xz = S(ab.tilt[1]);
+    b.yz = S(ab.tilt[2]);
+    b.flags = 0;
+    return b;
+    }
+
 template<class S> static NlistArgs<S> convert(const azp_nlist_args& a)
     {
     NlistArgs<S> k;
     k.pos = static_cast<const S*>(a.d_pos);
     k.N = a.N;
     k.ntypes = a.ntypes;
+    k.box = nlist_box<S>(a.box);
     for (int d = 0; d < 3; ++d)
         {
-        k.box.L[d] = S(a.box.L[d]);
-        k.box.Linv[d] = S(1.0) / k.box.L[d];
-        k.box.periodic[d] = a.box.periodic[d];
         k.grid.dim[d] = a.cell_dim[d];
         k.grid.reach[d] = a.cell_dim[d] >= 3 ? 1 : 0;
         }
-    k.box.xy = k.box.xz = k.box.yz = S(0);
-    k.box.flags = 0;
     k.rlistsq = static_cast<const S*>(a.d_rlistsq);
     k.n_neigh = a.d_n_neigh;
     k.head_list = a.d_head_list;
@@ -175,6 +267,8 @@ template<class S> static NlistArgs<S> convert(const azp_nlist_args& a)
     k.cell_of = a.d_cell_of;
     k.cell_start = a.d_cell_start;
     k.cell_order = a.d_cell_order;
+    k.cell_pos = static_cast<S*>(a.d_cell_pos);
+    k.pos_at_build = static_cast<S*>(a.d_pos_at_build);
     k.row_offset = a.n_rows ? a.row_offset : 0u;
     k.n_rows = a.n_rows ? a.n_rows : a.N;
     k.capacity = a.d_capacity;
@@ -184,10 +278,8 @@ template<class S> static NlistArgs<S> convert(const azp_nlist_args& a)
 
 static bool valid_common(const azp_nlist_args* a)
     {
-    if (!a || !a->d_pos || !a->d_rlistsq || !a->d_cell_of || !a->d_cell_start || !a->d_cell_order)
+    if (!a || !a->d_pos || !a->d_rlistsq || !a->d_cell_of || !a->d_cell_start || !a->d_cell_order || !a->d_cell_pos)
         return false;
-    if (a->box.tilt[0] != 0 || a->box.tilt[1] != 0 || a->box.tilt[2] != 0)
-        return false; // orthorhombic boxes only
     for (int d = 0; d < 3; ++d)
         if (a->cell_dim[d] == 0 || a->cell_dim[d] == 2)
             return false;
@@ -225,12 +317,21 @@ template<class S> static int bin(const azp_nlist_args* a, cudaStream_t st)
         {
         cub::DeviceRadixSort::SortPairs(temp, temp_bytes, a->d_cell_of, sorted_cells, iota, a->d_cell_order, (int)a->N, 0, bits, st);
         nlist_cell_starts<<<(ncells + 1 + block - 1) / block, block, 0, st>>>(sorted_cells, a->N, ncells, a->d_cell_start);
+        nlist_sorted_positions<S><<<(a->N + block - 1) / block, block, 0, st>>>(k);
         err = cudaGetLastError();
         cudaFreeAsync(temp, st);
         }
     cudaFreeAsync(sorted_cells, st);
     cudaFreeAsync(iota, st);
     return (int)err;
+    }
+
+template<class S, bool FILL, unsigned int TPP> static int rows_tpp(const NlistArgs<S>& k, cudaStream_t st)
+    {
+    const unsigned int block = 128;
+    const unsigned long long threads = (unsigned long long)k.n_rows * TPP;
+    nlist_rows<S, FILL, TPP><<<(unsigned int)((threads + block - 1) / block), block, 0, st>>>(k);
+    return (int)cudaGetLastError();
     }
 
 template<class S, bool FILL> static int rows(const azp_nlist_args* a, cudaStream_t st)
@@ -246,9 +347,102 @@ template<class S, bool FILL> static int rows(const azp_nlist_args* a, cudaStream
     const NlistArgs<S> k = convert<S>(*a);
     if ((unsigned long long)k.row_offset + k.n_rows > a->N)
         return (int)cudaErrorInvalidValue;
-    const unsigned int block = 128;
-    nlist_rows<S, FILL><<<(k.n_rows + block - 1) / block, block, 0, st>>>(k);
-    return (int)cudaGetLastError();
+    // lanes per row from the mean cell population (candidates per stencil cell): a cell is
+    // swept TPP candidates at a time
+    const double per_cell = double(a->N) / (double(a->cell_dim[0]) * a->cell_dim[1] * a->cell_dim[2]);
+    unsigned int tpp = a->threads_per_row;
+    if (tpp == 0)
+        tpp = per_cell > 24.0 ? 16u : (per_cell > 6.0 ? 8u : 4u);
+    switch (tpp)
+        {
+    case 1:
+        return rows_tpp<S, FILL, 1>(k, st);
+    case 2:
+        return rows_tpp<S, FILL, 2>(k, st);
+    case 4:
+        return rows_tpp<S, FILL, 4>(k, st);
+    case 8:
+        return rows_tpp<S, FILL, 8>(k, st);
+    case 16:
+        return rows_tpp<S, FILL, 16>(k, st);
+    case 32:
+        return rows_tpp<S, FILL, 32>(k, st);
+    default:
+        return (int)cudaErrorInvalidValue;
+        }
+    }
+
+// Displacement check on the device (HOOMD NeighborList::distanceCheck): *flag is raised when any
+// particle has moved farther than sqrt(maxsq) from its position at the last build (minimum
+// image, so a particle that was wrapped across a face does not count as moved).
+template<class S> __global__ void nlist_moved(const S* __restrict__ pos, const S* __restrict__ pos_at_build, const BoxDim<S> box, const S maxsq, const unsigned int N, unsigned int* flag)
+    {
+    const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool moved = false;
+    if (i < N)
+        {
+        const Vec4<S> p = load4(pos, i);
+        const Vec4<S> q = load4(pos_at_build, i);
+        S x = p.x - q.x, y = p.y - q.y, z = p.z - q.z;
+        min_image_general(box, x, y, z);
+        moved = x * x + y * y + z * z > maxsq;
+        }
+    if (__any_sync(0xffffffffu, moved) && (threadIdx.x & 31u) == 0)
+        atomicMax(flag, 1u);
+    }
+
+// Morton (Z-order) key of a position: 10 bits per axis of the fractional coordinate
+template<class S> __global__ void sfc_keys(const S* __restrict__ pos, const BoxDim<S> box, const unsigned int N, unsigned int* keys, unsigned int* iota)
+    {
+    const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N)
+        return;
+    const Vec4<S> p = load4(pos, i);
+    CellGrid g;
+    g.dim[0] = g.dim[1] = g.dim[2] = 1024u;
+    int c[3];
+    cell_coords(box, g, p.x, p.y, p.z, c);
+    unsigned int key = 0;
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+        {
+        unsigned int v = (unsigned int)c[d] & 0x3ffu;
+        v = (v | (v << 16)) & 0x030000ffu;
+        v = (v | (v << 8)) & 0x0300f00fu;
+        v = (v | (v << 4)) & 0x030c30c3u;
+        v = (v | (v << 2)) & 0x09249249u;
+        key |= v << d;
+        }
+    keys[i] = key;
+    iota[i] = i;
+    }
+
+template<class S> static int sfc_order(const void* d_pos, const azp_box* box, unsigned int N, unsigned int* d_order, cudaStream_t st)
+    {
+    if (!d_pos || !box || !d_order)
+        return (int)cudaErrorInvalidValue;
+    if (N == 0)
+        return 0;
+    unsigned int *keys = nullptr, *keys_out = nullptr, *iota = nullptr;
+    void* temp = nullptr;
+    size_t temp_bytes = 0;
+    cudaError_t err = cudaMallocAsync(&keys, 3 * sizeof(unsigned int) * (size_t)N, st);
+    if (err != cudaSuccess)
+        return (int)err;
+    keys_out = keys + N;
+    iota = keys + 2 * (size_t)N;
+    const unsigned int block = 256;
+    sfc_keys<S><<<(N + block - 1) / block, block, 0, st>>>(static_cast<const S*>(d_pos), nlist_box<S>(*box), N, keys, iota);
+    cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, keys, keys_out, iota, d_order, (int)N, 0, 30, st);
+    err = cudaMallocAsync(&temp, temp_bytes, st);
+    if (err == cudaSuccess)
+        {
+        cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys, keys_out, iota, d_order, (int)N, 0, 30, st);
+        err = cudaGetLastError();
+        cudaFreeAsync(temp, st);
+        }
+    cudaFreeAsync(keys, st);
+    return (int)err;
     }
     } // namespace azp
 
@@ -317,19 +511,54 @@ extern "C"
 
     // Largest grid with cells no smaller than r_list_max. An axis that cannot hold three such
     // cells gets a single cell (the stencil then covers it once and minimum image does the rest).
+    // Triclinic boxes: the cell width is measured between the lattice planes (HOOMD's
+    // BoxDim::getNearestPlaneDistance).
     int azp_nlist_cell_dim(const azp_box* box, double r_list_max, uint32_t dim[3])
         {
         if (!box || !dim || !(r_list_max > 0))
             return (int)cudaErrorInvalidValue;
+        const double xy = box->tilt[0], xz = box->tilt[1], yz = box->tilt[2];
+        const double t = xy * yz - xz;
+        const double plane[3] = {box->L[0] / sqrt(1.0 + xy * xy + t * t), box->L[1] / sqrt(1.0 + yz * yz), box->L[2]};
         for (int d = 0; d < 3; ++d)
             {
-            const double n = box->L[d] / r_list_max;
+            const double n = plane[d] / r_list_max;
             uint32_t c = n >= 3.0 ? (uint32_t)n : 1u;
             if (c > 1024u)
                 c = 1024u;
             dim[d] = c;
             }
         return 0;
+        }
+    int azp_nlist_moved_f32(const void* d_pos, const void* d_pos_at_build, const azp_box* box, double max_dist, uint32_t N, uint32_t* d_flag, void* st)
+        {
+        if (!d_pos || !d_pos_at_build || !box || !d_flag)
+            return (int)cudaErrorInvalidValue;
+        if (N == 0)
+            return 0;
+        azp::BoxDim<float> b = azp::nlist_box<float>(*box);
+        b.flags = (box->tilt[0] != 0 || box->tilt[1] != 0 || box->tilt[2] != 0) ? 1 : 0;
+        azp::nlist_moved<float><<<(N + 255u) / 256u, 256, 0, (cudaStream_t)st>>>(static_cast<const float*>(d_pos), static_cast<const float*>(d_pos_at_build), b, float(max_dist * max_dist), N, d_flag);
+        return (int)cudaGetLastError();
+        }
+    int azp_nlist_moved_f64(const void* d_pos, const void* d_pos_at_build, const azp_box* box, double max_dist, uint32_t N, uint32_t* d_flag, void* st)
+        {
+        if (!d_pos || !d_pos_at_build || !box || !d_flag)
+            return (int)cudaErrorInvalidValue;
+        if (N == 0)
+            return 0;
+        azp::BoxDim<double> b = azp::nlist_box<double>(*box);
+        b.flags = (box->tilt[0] != 0 || box->tilt[1] != 0 || box->tilt[2] != 0) ? 1 : 0;
+        azp::nlist_moved<double><<<(N + 255u) / 256u, 256, 0, (cudaStream_t)st>>>(static_cast<const double*>(d_pos), static_cast<const double*>(d_pos_at_build), b, max_dist * max_dist, N, d_flag);
+        return (int)cudaGetLastError();
+        }
+    int azp_sfc_order_f32(const void* d_pos, const azp_box* box, uint32_t N, uint32_t* d_order, void* st)
+        {
+        return azp::sfc_order<float>(d_pos, box, N, d_order, (cudaStream_t)st);
+        }
+    int azp_sfc_order_f64(const void* d_pos, const azp_box* box, uint32_t N, uint32_t* d_order, void* st)
+        {
+        return azp::sfc_order<double>(d_pos, box, N, d_order, (cudaStream_t)st);
         }
     int azp_nlist_bin_f32(const azp_nlist_args* a, void* st)
         {

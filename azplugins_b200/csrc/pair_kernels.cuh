@@ -45,6 +45,10 @@
 #ifndef AZP_TRIP_WRAP
 #define AZP_TRIP_WRAP 0
 #endif
+// queued neighbours a lane evaluates per heavy round of the deferred-accept families (1 or 2)
+#ifndef AZP_HEAVY_UNROLL
+#define AZP_HEAVY_UNROLL 1
+#endif
 
 namespace azp
     {
@@ -813,32 +817,50 @@ template<class E_, class S_, bool VIRIAL, int NTM_> struct DpdFamily
             }
         }
 
-    // heavy part, one queued neighbour per lane (lanes with an empty queue idle)
+    // heavy part: up to AZP_HEAVY_UNROLL queued neighbours per lane and round (lanes with an
+    // empty queue idle). Velocity and tag are only needed for accepted pairs (about a third of
+    // the list at buffer 0.4), so they are gathered here, behind the scan's cutoff test --
+    // together with the position, and for all neighbours of the round before any of them is
+    // evaluated, so that a round exposes ONE gather latency (the few entries inside the scan's
+    // ulp margin but outside the cutoff load them in vain).
+    AZP_D void heavy_one(const KernelArgs<S>& a, const RowGeometry<S>& g, const Vec4<S>& pj, const Vec4<S>& vj, unsigned int tag_j)
+        {
+        S dx, dy, dz;
+        g.displacement(a.box, pj, dx, dy, dz);
+        // rsq = dot(dx, dx) rounded like the reference's host loop (no FMA): for s < 2 the
+        // weight is not continuous in the last ulp below the cutoff (eval_dpd.cuh), so
+        // both the cutoff decision and r must see the reference's rsq
+        const S rsq = ref::dot3(dx, dy, dz, dx, dy, dz);
+        const unsigned int tj = NTM == 1 ? 0u : scalar_as_uint(pj.w);
+        const S rcutsq = types.rcutsq(tj);
+        if (rsq < rcutsq)
+            {
+            const Cache c = types.cache(tj);
+            accept(a, c, vj, tag_j, rsq, rcutsq, dx, dy, dz);
+            }
+        }
     AZP_D void heavy(const KernelArgs<S>& a, const RowGeometry<S>& g)
         {
-        if (queue.n > 0u)
+        const unsigned int pending = queue.n;
+        if (pending > 0u)
             {
-            // velocity and tag are only needed for accepted pairs (about a third of the list at
-            // buffer 0.4), so they are gathered here, behind the scan's cutoff test -- together
-            // with the position, so that a round exposes one gather latency instead of two (the
-            // few entries inside the scan's ulp margin but outside the cutoff load them in vain)
-            const unsigned int j = queue.pop();
-            const Vec4<S> pj = load4(a.pos, j);
-            const Vec4<S> vj = load4(a.vel, j);
-            const unsigned int tag_j = __ldg(a.tag + j);
-            S dx, dy, dz;
-            g.displacement(a.box, pj, dx, dy, dz);
-            // rsq = dot(dx, dx) rounded like the reference's host loop (no FMA): for s < 2 the
-            // weight is not continuous in the last ulp below the cutoff (eval_dpd.cuh), so
-            // both the cutoff decision and r must see the reference's rsq
-            const S rsq = ref::dot3(dx, dy, dz, dx, dy, dz);
-            const unsigned int tj = NTM == 1 ? 0u : scalar_as_uint(pj.w);
-            const S rcutsq = types.rcutsq(tj);
-            if (rsq < rcutsq)
+            const unsigned int j0 = queue.pop();
+            const bool two = AZP_HEAVY_UNROLL > 1 && pending > 1u;
+            const unsigned int j1 = two ? queue.pop() : j0;
+            const Vec4<S> p0 = load4(a.pos, j0);
+            const Vec4<S> v0 = load4(a.vel, j0);
+            const unsigned int t0 = __ldg(a.tag + j0);
+            if (AZP_HEAVY_UNROLL > 1)
                 {
-                const Cache c = types.cache(tj);
-                accept(a, c, vj, tag_j, rsq, rcutsq, dx, dy, dz);
+                const Vec4<S> p1 = load4(a.pos, j1);
+                const Vec4<S> v1 = load4(a.vel, j1);
+                const unsigned int t1 = __ldg(a.tag + j1);
+                heavy_one(a, g, p0, v0, t0);
+                if (two)
+                    heavy_one(a, g, p1, v1, t1);
                 }
+            else
+                heavy_one(a, g, p0, v0, t0);
             }
         }
 
@@ -987,20 +1009,37 @@ template<class E_, class S_, bool VIRIAL, int NTM_> struct AnisoFamily
 #endif
             }
         }
+    AZP_D void heavy_one(const KernelArgs<S>& a, const RowGeometry<S>& g, const Vec4<S>& pj, const Vec4<S>& qj)
+        {
+        Vec3<S> dr;
+        g.displacement(a.box, pj, dr.x, dr.y, dr.z);
+        const S rsq = fma(dr.z, dr.z, fma(dr.y, dr.y, dr.x * dr.x));
+        const unsigned int tj = NTM == 1 ? 0u : scalar_as_uint(pj.w);
+        accept(types.cache(tj), qj, rsq, types.rcutsq(tj), dr);
+        }
     AZP_D void heavy(const KernelArgs<S>& a, const RowGeometry<S>& g)
         {
-        if (queue.n > 0u)
+        // all gathers of the round (position + orientation of up to AZP_HEAVY_UNROLL queued
+        // neighbours) are issued together: one exposed latency per round; the scan applied
+        // pair()'s own cutoff test to the same displacement, so it is not repeated
+        const unsigned int pending = queue.n;
+        if (pending > 0u)
             {
-            // both gathers of the round are issued together (one exposed latency, not two); the
-            // scan applied pair()'s own cutoff test to the same displacement, so it is not repeated
-            const unsigned int j = queue.pop();
-            const Vec4<S> pj = load4(a.pos, j);
-            const Vec4<S> qj = load4(a.orientation, j);
-            Vec3<S> dr;
-            g.displacement(a.box, pj, dr.x, dr.y, dr.z);
-            const S rsq = fma(dr.z, dr.z, fma(dr.y, dr.y, dr.x * dr.x));
-            const unsigned int tj = NTM == 1 ? 0u : scalar_as_uint(pj.w);
-            accept(types.cache(tj), qj, rsq, types.rcutsq(tj), dr);
+            const unsigned int j0 = queue.pop();
+            const bool two = AZP_HEAVY_UNROLL > 1 && pending > 1u;
+            const unsigned int j1 = two ? queue.pop() : j0;
+            const Vec4<S> p0 = load4(a.pos, j0);
+            const Vec4<S> q0 = load4(a.orientation, j0);
+            if (AZP_HEAVY_UNROLL > 1)
+                {
+                const Vec4<S> p1 = load4(a.pos, j1);
+                const Vec4<S> q1 = load4(a.orientation, j1);
+                heavy_one(a, g, p0, q0);
+                if (two)
+                    heavy_one(a, g, p1, q1);
+                }
+            else
+                heavy_one(a, g, p0, q0);
             }
         }
 

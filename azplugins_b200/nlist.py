@@ -35,6 +35,7 @@ class NeighborList:
         self.n_max = 0  # largest row capacity (HOOMD's n_max)
         self.num_builds = 0
         self._pos_at_build = None
+        self._moved_flag = None
         self._external = False
         self._frozen = False      # freeze(): benchmarks / graph capture keep the current list
         self._built_for = None    # (box, r_list matrix) of the last build
@@ -128,11 +129,18 @@ class NeighborList:
             return True  # check_dist=False: rebuild at every check (HOOMD semantics)
         if self._pos_at_build.shape != state.pos.shape:
             return True
-        d = state.pos[:, :3] - self._pos_at_build[:, :3]
-        L = torch.tensor(state.box.L, dtype=d.dtype, device=d.device)
-        per = torch.tensor([float(p) for p in state.box.periodic], dtype=d.dtype, device=d.device)
-        d = d - per * L * torch.round(d / L)
-        return bool((d * d).sum(dim=1).max() > (0.5 * self.buffer) ** 2)
+        # device-side check (azp_nlist_moved): one kernel and one 4-byte read-back
+        if self._moved_flag is None or self._moved_flag.device != state.pos.device:
+            self._moved_flag = torch.zeros(1, dtype=torch.int32, device=state.pos.device)
+        self._moved_flag.zero_()
+        box = state.box.to_c()
+        with torch.cuda.device(state.device):
+            stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+            fn = getattr(_lib.lib, "azp_nlist_moved_f%d" % (8 * state.dtype.itemsize))
+            _lib.check(fn(state.pos.data_ptr(), self._pos_at_build.data_ptr(), ctypes.byref(box),
+                          0.5 * self.buffer, state.pos.shape[0], self._moved_flag.data_ptr(), stream),
+                       "nlist moved")
+        return bool(self._moved_flag.item())
 
     def to_numpy(self):
         return (self.n_neigh.cpu().numpy().view(np.uint32),
@@ -144,10 +152,11 @@ class Cell(NeighborList):
     """Cell-list neighbour search on the GPU; ctor mirrors ``hoomd.md.nlist.Cell``."""
 
     def __init__(self, buffer, exclusions=("bond",), rebuild_check_delay=1, check_dist=True,
-                 deterministic=False, mesh=None, default_r_cut=0.0, row_align=8):
+                 deterministic=False, mesh=None, default_r_cut=0.0, row_align=8, threads_per_row=0):
         super().__init__(buffer, exclusions, rebuild_check_delay, check_dist, default_r_cut)
         self.deterministic = deterministic
         self.row_align = int(row_align)
+        self.threads_per_row = int(threads_per_row)  # lanes per row of the builder (0 = library choice)
         self.reuse_capacity = True  # skip the count pass while the previous row capacities suffice
 
     def build(self, state, rows=None):
@@ -164,8 +173,8 @@ class Cell(NeighborList):
         r_max = float(r_list.max())
         if not r_max > 0:
             raise ValueError("neighbour list has no positive r_cut")
-        for d in range(3):
-            if state.box.periodic[d] and state.box.L[d] < 2.0 * r_max:
+        for d, width in enumerate(state.box.nearest_plane_distance()):
+            if state.box.periodic[d] and width < 2.0 * r_max:
                 raise ValueError("box too small for r_cut + buffer (minimum image)")
         dev = state.device
         n_total = state.pos.shape[0]
@@ -190,6 +199,10 @@ class Cell(NeighborList):
             cell_of = torch.empty(n_total, dtype=torch.int32, device=dev)
             cell_start = torch.empty(ncells + 1, dtype=torch.int32, device=dev)
             cell_order = torch.empty(n_total, dtype=torch.int32, device=dev)
+            cell_pos = torch.empty_like(state.pos)
+            if (self._pos_at_build is None or self._pos_at_build.shape != state.pos.shape
+                    or self._pos_at_build.dtype != state.pos.dtype or self._pos_at_build.device != dev):
+                self._pos_at_build = torch.empty_like(state.pos)
             # persistent buffers where the shape allows: consumers that recorded device
             # addresses (a CUDA graph of the MD step) stay valid across rebuilds
             if (self.n_neigh is not None and not self._external and self.n_neigh.numel() == n_rows
@@ -202,6 +215,9 @@ class Cell(NeighborList):
             a.d_cell_of = cell_of.data_ptr()
             a.d_cell_start = cell_start.data_ptr()
             a.d_cell_order = cell_order.data_ptr()
+            a.d_cell_pos = cell_pos.data_ptr()
+            a.d_pos_at_build = self._pos_at_build.data_ptr()  # bin copies the positions there
+            a.threads_per_row = self.threads_per_row
             a.d_n_neigh = n_neigh.data_ptr()
             _lib.check(getattr(_lib.lib, "azp_nlist_bin" + sfx)(ctypes.byref(a), stream), "nlist bin")
             # Capacity reuse (what HOOMD's NeighborList does between builds): when the previous
@@ -245,7 +261,6 @@ class Cell(NeighborList):
             self.num_reused = getattr(self, "num_reused", 0) + int(reused)
         # rows of ghosts are built too but only the first N rows are consumed
         self.n_neigh, self.nlist, self.head_list, self.size = n_neigh, nlist, head, size
-        self._pos_at_build = state.pos.clone()
         self.num_builds += 1
 
 

@@ -86,5 +86,28 @@ class State:
     def type_index(self, name):
         return self.types.index(name)
 
+    def sfc_sort(self):
+        """Reorder the particles along a Morton curve on the device (what HOOMD's SFCPackTuner
+        does to ParticleData): ``pos``, ``vel``, ``orientation`` and ``tag`` are permuted together,
+        so spatial neighbours become memory neighbours and the position gathers of the force
+        kernels stay L1/L2-resident. Returns the permutation (new index -> old index). Neighbour
+        lists and per-particle outputs refer to the old order: rebuild / recompute afterwards."""
+        import ctypes
+
+        from . import _lib
+
+        n = self.pos.shape[0] - self.n_ghost
+        order = torch.empty(n, dtype=torch.int32, device=self.device)
+        box = self.box.to_c()
+        with torch.cuda.device(self.device):
+            stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+            fn = getattr(_lib.lib, "azp_sfc_order_f%d" % (8 * self.dtype.itemsize))
+            _lib.check(fn(self.pos.data_ptr(), ctypes.byref(box), n, order.data_ptr(), stream), "sfc order")
+        idx = order.to(torch.int64)
+        for name in ("pos", "vel", "orientation", "tag"):
+            arr = getattr(self, name)
+            arr[:n] = arr[:n].index_select(0, idx)
+        return idx
+
     def positions_numpy(self):
         return self.pos.cpu().numpy()[:, :3].copy()

@@ -351,6 +351,10 @@ typedef struct azp_nlist_args
      * count + fill. NULL = exact fill after the count pass; d_n_neigh is then not written. */
     const uint32_t* d_capacity;
     uint32_t* d_overflow;
+    void* d_cell_pos;         /* Scalar4[N] scratch: positions in cell order (written by bin) */
+    void* d_pos_at_build;     /* Scalar4[N] or NULL: bin copies d_pos here for azp_nlist_moved */
+    uint32_t threads_per_row; /* lanes per row in count / fill: 0 = library choice, else 1..32 (2^k) */
+    uint32_t _pad2;
     } azp_nlist_args;
 
 int azp_nlist_cell_dim(const azp_box* box, double r_list_max, uint32_t dim[3]);
@@ -360,6 +364,16 @@ int azp_nlist_count_f32(const azp_nlist_args* args, void* stream);
 int azp_nlist_count_f64(const azp_nlist_args* args, void* stream);
 int azp_nlist_fill_f32(const azp_nlist_args* args, void* stream);
 int azp_nlist_fill_f64(const azp_nlist_args* args, void* stream);
+/* Displacement check on the device (HOOMD NeighborList::distanceCheck): *d_flag (zeroed by the
+ * caller) is raised when some particle is farther than max_dist (= buffer / 2) from its position
+ * at the last build, minimum image applied. */
+int azp_nlist_moved_f32(const void* d_pos, const void* d_pos_at_build, const azp_box* box, double max_dist, uint32_t N, uint32_t* d_flag, void* stream);
+int azp_nlist_moved_f64(const void* d_pos, const void* d_pos_at_build, const azp_box* box, double max_dist, uint32_t N, uint32_t* d_flag, void* stream);
+/* Space-filling-curve order of the particles (what HOOMD's SFCPackTuner applies to ParticleData so
+ * that neighbours in space are neighbours in memory): d_order[k] = index of the particle that
+ * comes k-th along a 30-bit Morton curve through the box. The caller permutes its arrays. */
+int azp_sfc_order_f32(const void* d_pos, const azp_box* box, uint32_t N, uint32_t* d_order, void* stream);
+int azp_sfc_order_f64(const void* d_pos, const azp_box* box, uint32_t N, uint32_t* d_order, void* stream);
 
 #ifdef __cplusplus
     }

@@ -16,7 +16,8 @@ def test_fused_colloid_hertz_equals_separate_launches(dtype, virial):
     import azplugins_b200 as az
     from azplugins_b200 import synth
 
-    wl = synth.config3(N=120000)
+    # 195 colloids on an 11.6-sigma lattice with jitter: 18 centre distances fall below the Hertz cutoff
+    wl = synth.config3(N=120000, n_colloid=6500)
     state = wl.make_state(dtype=dtype)
     nl = az.nlist.Cell(buffer=synth.BUFFER)
     colloid, hertz = wl.make_potentials(nl)

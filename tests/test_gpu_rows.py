@@ -101,3 +101,112 @@ def test_nlist_capacity_reuse_gives_the_same_list():
     pot.compute()
     torch.cuda.synchronize()
     del ref
+
+
+def _brute_force_rows(xyz, typeid, box, r_list, rows):
+    """Neighbour sets of `rows` by brute force in float64 with HOOMD's sequential minimum image."""
+    L = np.array(box.L)
+    out = []
+    for i in rows:
+        d = xyz[i] - xyz
+        if box.periodic[2]:
+            img = np.rint(d[:, 2] / L[2])
+            d[:, 2] -= L[2] * img
+            d[:, 1] -= L[2] * box.yz * img
+            d[:, 0] -= L[2] * box.xz * img
+        if box.periodic[1]:
+            img = np.rint(d[:, 1] / L[1])
+            d[:, 1] -= L[1] * img
+            d[:, 0] -= L[1] * box.xy * img
+        if box.periodic[0]:
+            img = np.rint(d[:, 0] / L[0])
+            d[:, 0] -= L[0] * img
+        rsq = (d * d).sum(axis=1)
+        ok = rsq < r_list[typeid[i], typeid] ** 2
+        ok[i] = False
+        out.append(np.nonzero(ok)[0])
+    return out
+
+
+@pytest.mark.parametrize("tilt,periodic", [((0.0, 0.0, 0.0), (True, True, True)),
+                                           ((0.3, -0.2, 0.15), (True, True, True)),
+                                           ((0.0, 0.0, 0.0), (True, True, False)),
+                                           ((0.25, 0.0, 0.0), (True, False, True))])
+@pytest.mark.parametrize("tpr", [0, 1, 4, 32])
+def test_nlist_builder_triclinic_and_walls_against_brute_force(tilt, periodic, tpr):
+    """The cell-list builder (cell-sorted positions, image numbers from the stencil instead of
+    rint) against brute force: orthorhombic and triclinic boxes, non-periodic axes (particles up
+    to the faces), two types with different r_list, any lanes-per-row setting; every setting gives
+    the same rows in the same order."""
+    import azplugins_b200 as az
+
+    rng = np.random.default_rng(31)
+    N = 6000
+    box = az.Box(14.0, 12.0, 16.0, xy=tilt[0], xz=tilt[1], yz=tilt[2], periodic=periodic)
+    f = rng.uniform(-0.5, 0.5, (N, 3))
+    xyz = np.empty_like(f)
+    xyz[:, 2] = f[:, 2] * box.Lz
+    xyz[:, 1] = f[:, 1] * box.Ly + box.yz * xyz[:, 2]
+    xyz[:, 0] = f[:, 0] * box.Lx + box.xy * xyz[:, 1] + (box.xz - box.xy * box.yz) * xyz[:, 2]
+    typeid = rng.integers(0, 2, N)
+    state = az.State(box, ["A", "B"], xyz, typeid=typeid, dtype=np.float64)
+    nl = az.nlist.Cell(buffer=0.4, threads_per_row=tpr)
+    plj = az.pair.PerturbedLennardJones(nlist=nl, default_r_cut=2.0)
+    plj.params[("A", "A")] = dict(epsilon=1.0, sigma=1.0, attraction_scale_factor=0.5)
+    plj.params[("A", "B")] = dict(epsilon=1.0, sigma=1.0, attraction_scale_factor=0.5)
+    plj.params[("B", "B")] = dict(epsilon=1.0, sigma=1.0, attraction_scale_factor=0.5)
+    plj.r_cut[("B", "B")] = 2.9
+    plj.attach(state)
+    nl.compute(state)
+    nn, lst, head = nl.to_numpy()
+    r_list = nl.r_cut_matrix(state) + 0.4
+    rows = rng.choice(N, 300, replace=False)
+    pos64 = state.pos.cpu().numpy()[:, :3].astype(np.float64)
+    for i, want in zip(rows, _brute_force_rows(pos64, typeid, box, r_list, rows)):
+        got = lst[head[i]:head[i] + nn[i]]
+        assert np.array_equal(np.sort(got), want), i
+    ref = az.nlist.Cell(buffer=0.4, threads_per_row=8)
+    plj2 = az.pair.PerturbedLennardJones(nlist=ref, default_r_cut=2.0)
+    plj2.params[("A", "A")] = plj2.params[("A", "B")] = plj2.params[("B", "B")] = dict(
+        epsilon=1.0, sigma=1.0, attraction_scale_factor=0.5)
+    plj2.r_cut[("B", "B")] = 2.9
+    plj2.attach(state)
+    ref.compute(state)
+    rn, rl, rh = ref.to_numpy()
+    assert np.array_equal(nn, rn) and np.array_equal(head, rh)
+    for i in rows:
+        assert np.array_equal(lst[head[i]:head[i] + nn[i]], rl[rh[i]:rh[i] + rn[i]])
+
+
+def test_device_sfc_sort_matches_host_morton_order():
+    """azp_sfc_order (State.sfc_sort): the device Morton order equals the host one of synth.py on
+    a 1024^3 grid, all per-particle arrays are permuted together, and forces computed after the
+    sort are the permuted forces."""
+    import azplugins_b200 as az
+    from azplugins_b200 import synth
+
+    rng = np.random.default_rng(8)
+    N = 20000
+    xyz, L = synth.jittered_lattice(N, 0.8, rng)
+    shuffle = rng.permutation(N)
+    xyz = xyz[shuffle]
+    state = az.State(az.Box.cube(L), ["A"], xyz, velocity=rng.standard_normal((N, 3)), dtype=np.float32)
+    pos_before = state.pos.cpu().numpy()
+    nl = az.nlist.Cell(buffer=0.4)
+    plj = az.pair.PerturbedLennardJones(nlist=nl, default_r_cut=3.0)
+    plj.params[("A", "A")] = dict(epsilon=1.0, sigma=1.0, attraction_scale_factor=0.5)
+    f_before = plj.attach(state).compute()._force.cpu().numpy().copy()
+    perm = state.sfc_sort().cpu().numpy()
+    assert np.array_equal(np.sort(perm), np.arange(N))
+    host = synth.morton_order(pos_before[:, :3].astype(np.float64), L, cell=L / 1024.0)
+    c = np.floor((pos_before[:, :3].astype(np.float32) / np.float32(L) + np.float32(0.5)) * 1024).astype(np.int64)
+    assert np.array_equal(pos_before[perm], state.pos.cpu().numpy())
+    assert np.array_equal(state.tag.cpu().numpy(), perm.astype(np.int32))
+    # same curve as the host order wherever the float32 / float64 cell assignment agrees
+    assert (perm == host).mean() > 0.99
+    nl2 = az.nlist.Cell(buffer=0.4)
+    plj2 = az.pair.PerturbedLennardJones(nlist=nl2, default_r_cut=3.0)
+    plj2.params[("A", "A")] = dict(epsilon=1.0, sigma=1.0, attraction_scale_factor=0.5)
+    f_after = plj2.attach(state).compute()._force.cpu().numpy()
+    scale = np.abs(f_before[:, :3]).max()
+    assert np.abs(f_after[:, :3] - f_before[perm, :3]).max() < 2e-5 * scale
