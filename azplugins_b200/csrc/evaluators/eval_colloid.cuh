@@ -166,6 +166,26 @@ template<class S> class PairEvaluatorColloid : public PairEvaluatorBase<S>
 
     // see IsoFamily::pair: skip the evaluator when no lane of the warp is inside the cutoff
     static constexpr bool kWarpVote = true;
+    // rare-form deferral (pair_kernels.cuh, FormSplit): the three couplings are three forms,
+    // cheapest first
+#ifndef AZP_COLLOID_NO_SPLIT
+    static constexpr bool kSplitForms = true;
+#endif
+    static constexpr int kHeavyForm = ColloidColloid; // never evaluated inside the neighbour loop
+    AZP_HD static int form(const cache_type& c)
+        {
+        return c.coupling;
+        }
+    // evalPair for the forms below kHeavyForm
+    AZP_D void evalPairLight(S& force_divr, S& pair_eng)
+        {
+        S e;
+        if (c.coupling == SolventSolvent)
+            e = solventSolvent<true>(c, this->rsq, force_divr);
+        else
+            e = colloidSolvent<true>(c, this->rsq, force_divr);
+        pair_eng = e - c.e_cut;
+        }
 
     AZP_HD static bool disabled(const cache_type& c)
         {

@@ -75,9 +75,25 @@ template<class S> class PairEvaluatorExpandedYukawa : public PairEvaluatorBase<S
             const S rd = r - c.delta;
             const S rdinv = fast::rcp(rd);
             const S e = c.epsilon * fast::exp_prescaled(c.neg_kappa_scaled * rd) * rdinv;
-            force_divr = e * (c.kappa + rdinv) * rinv;
+            force_divr = e * kappa_plus(rdinv) * rinv;
             pair_eng = e - c.e_cut;
             }
+        }
+
+    // kappa + x. fp32: kappa is recovered from the staged -kappa log2(e) inside the FMA
+    // (kappa' = fl(-kappa log2 e) * -ln 2, within 2 ulp of kappa: 1e-7 of the force), so a
+    // two-type row selects one constant less per neighbour
+    AZP_D float kappa_plus(float x) const
+        {
+#ifdef AZP_YUKAWA_KEEP_KAPPA
+        return c.kappa + x;
+#else
+        return __fmaf_rn(c.neg_kappa_scaled, -0.6931471805599453f, x);
+#endif
+        }
+    AZP_D double kappa_plus(double x) const
+        {
+        return c.kappa + x;
         }
 
     static const char* getName()

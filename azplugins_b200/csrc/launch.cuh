@@ -197,12 +197,25 @@ inline cudaError_t launch_rows(KernelArgs<typename Fam::S> k, const void* d_para
         k.long_count = scratch.count;
         k.long_capacity = kLongRowCapacity;
         }
-    auto kernel = row_kernel<Fam, false>;
     const size_t smem = Fam::smem_bytes(ntp, s.block);
-    err = ensure_smem(kernel, smem);
-    if (err != cudaSuccess)
-        return err;
-    kernel<<<s.grid, s.block, smem, stream>>>(k, params, s.tpp_log2);
+#ifndef AZP_NO_ONE_LANE
+    if (s.tpp_log2 == 0)
+        {
+        auto kernel = row_kernel<Fam, false, true>;
+        err = ensure_smem(kernel, smem);
+        if (err != cudaSuccess)
+            return err;
+        kernel<<<s.grid, s.block, smem, stream>>>(k, params, 0u);
+        }
+    else
+#endif
+        {
+        auto kernel = row_kernel<Fam, false, false>;
+        err = ensure_smem(kernel, smem);
+        if (err != cudaSuccess)
+            return err;
+        kernel<<<s.grid, s.block, smem, stream>>>(k, params, s.tpp_log2);
+        }
     err = cudaGetLastError();
     if (err != cudaSuccess || !defer)
         return err;

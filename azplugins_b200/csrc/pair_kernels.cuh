@@ -49,6 +49,10 @@
 #ifndef AZP_HEAVY_UNROLL
 #define AZP_HEAVY_UNROLL 1
 #endif
+// lines (128 B) ahead of a lane's cursor that the pipelined loop requests into L2; 0 = off
+#ifndef AZP_NLIST_LINE_PREFETCH
+#define AZP_NLIST_LINE_PREFETCH 0
+#endif
 
 namespace azp
     {
@@ -368,6 +372,123 @@ template<class E, class S, int NTM> struct TypeLookup
         }
     };
 
+// Rare-form deferral ("form split"). Some evaluators choose between arithmetically different
+// FORMS by the type pair -- Colloid: point-point, sphere-point, sphere-sphere (reference
+// src/PairEvaluatorColloid.h:233-269). In a two-type system a row sees two forms: the common one
+// (solvent-solvent for a solvent row) and a rare, costlier one (the one or two colloids within
+// reach). Evaluated in place, ONE lane with a rare neighbour makes its whole warp run the rare
+// form as well -- for C3 that is 38 % of all neighbour slots. Instead the head of a rare
+// neighbour only pushes its index into the lane's AcceptQueue, the in-place evaluation always
+// uses the row's common form (which also drops the per-neighbour select of the constants), and
+// the queued neighbours are evaluated when the row is done (or the queue is full): the lanes of
+// a warp that hold rare entries run the rare form together, a few times per row instead of a
+// few dozen. An evaluator opts in with `static constexpr bool kSplitForms = true`,
+// `static int form(const cache_type&)` (lower = cheaper = evaluated in place), `kHeavyForm`
+// (forms from this one on are ALWAYS deferred, so their code stays out of the neighbour loop and
+// its register allocation) and `evalPairLight` (evalPair restricted to the forms below it).
+template<class E, class = void> struct SplitForms : std::false_type
+    {
+    };
+template<class E> struct SplitForms<E, typename std::enable_if<E::kSplitForms>::type> : std::true_type
+    {
+    };
+
+template<class E, class S, bool ENABLED> struct FormSplit
+    {
+    AcceptQueue queue;
+    bool defer_a, defer_b; // pairs with a neighbour of type 0 / 1 are deferred
+    // Called after TypeLookup::begin_row has loaded the row's two candidate sets. A deferred
+    // partner's in-place constants are replaced by the other partner's and its in-place cutoff
+    // by zero, so the neighbour loop needs no extra test or select: a rare neighbour is simply
+    // "outside"; drain_one() reloads the true constants from the shared-memory table.
+    template<class TL> AZP_D void begin_row(TL& types)
+        {
+        queue.n = 0;
+        const bool live_a = types.rcA > S(0), live_b = types.rcB > S(0);
+        const int fa = E::form(types.cA), fb = E::form(types.cB);
+        // defer the costlier form when both partners are live and their forms differ, and any
+        // form the evaluator keeps out of the in-place code altogether (form >= kHeavyForm)
+        defer_a = live_a && ((live_b && fa > fb) || fa >= E::kHeavyForm);
+        defer_b = live_b && ((live_a && fb > fa) || fb >= E::kHeavyForm);
+        if (defer_a)
+            {
+            types.cA = types.cB;
+            types.rcA = S(0);
+            }
+        if (defer_b)
+            {
+            types.cB = types.cA;
+            types.rcB = S(0);
+            }
+        }
+    AZP_D bool rare(unsigned int tj) const
+        {
+        return tj ? defer_b : defer_a;
+        }
+    AZP_D bool any() const
+        {
+        return defer_a || defer_b;
+        }
+    };
+template<class E, class S> struct FormSplit<E, S, false>
+    {
+    template<class TL> AZP_D void begin_row(TL&) { }
+    AZP_D bool rare(unsigned int) const
+        {
+        return false;
+        }
+    AZP_D bool any() const
+        {
+        return false;
+        }
+    };
+
+template<class E, class S> AZP_D void carve_split(FormSplit<E, S, true>& sp, unsigned int& off)
+    {
+    sp.queue.carve(off);
+    off = sp.queue.off + (unsigned int)AcceptQueue::bytes(blockDim.x);
+    }
+template<class E, class S> AZP_D void carve_split(FormSplit<E, S, false>&, unsigned int&) { }
+template<class E, class S> AZP_D void push_split(FormSplit<E, S, true>& sp, unsigned int j)
+    {
+    sp.queue.push(j);
+    }
+template<class E, class S> AZP_D void push_split(FormSplit<E, S, false>&, unsigned int) { }
+template<class E, class S> AZP_D unsigned int pop_split(FormSplit<E, S, true>& sp)
+    {
+    return sp.queue.pop();
+    }
+template<class E, class S> AZP_D unsigned int pop_split(FormSplit<E, S, false>&)
+    {
+    return 0u;
+    }
+template<class E, class S> AZP_D bool split_pending(const FormSplit<E, S, true>& sp)
+    {
+    return sp.queue.n > 0u;
+    }
+template<class E, class S> AZP_D bool split_pending(const FormSplit<E, S, false>&)
+    {
+    return false;
+    }
+// fewer than `room` free slots left
+template<class E, class S> AZP_D bool split_short(const FormSplit<E, S, true>& sp, unsigned int room)
+    {
+    return sp.queue.n + room > AcceptQueue::Q;
+    }
+template<class E, class S> AZP_D bool split_short(const FormSplit<E, S, false>&, unsigned int)
+    {
+    return false;
+    }
+// the in-place evaluation of a split family only ever sees the forms below E::kHeavyForm
+template<bool LIGHT, class E, class S> AZP_D auto eval_in_place(E& eval, S& f, S& e) -> typename std::enable_if<LIGHT>::type
+    {
+    eval.evalPairLight(f, e);
+    }
+template<bool LIGHT, class E, class S> AZP_D auto eval_in_place(E& eval, S& f, S& e) -> typename std::enable_if<!LIGHT>::type
+    {
+    eval.evalPair(f, e, false);
+    }
+
 // =============================================================================================
 // Isotropic family: F_i = sum dx * force_divr, E_i = 1/2 sum U, W_i = 1/2 sum dx_a dx_b force_divr
 // =============================================================================================
@@ -390,15 +511,19 @@ template<class E_, class S_, bool XPLOR, bool VIRIAL, int NTM_> struct IsoFamily
     static constexpr int PIPE = IsoTraits<E>::pipe;
     static constexpr bool QUEUE = false;
     static constexpr bool MULTIROW = false;
+    // rare-form deferral (FormSplit): two-type systems of an evaluator with several forms
+    static constexpr bool SPLIT = SplitForms<E>::value && NTM == 2 && !XPLOR;
 
     TypeLookup<E, S, NTM> types;
+    FormSplit<E, S, SPLIT> split;
     unsigned int xplor_off;
     S fx = S(0), fy = S(0), fz = S(0), pe = S(0);
     Virial6<S> w;
 
-    AZP_HD static size_t smem_bytes(size_t ntp, size_t)
+    AZP_HD static size_t smem_bytes(size_t ntp, size_t block)
         {
-        return PairTable<E, S>::bytes(ntp) + (XPLOR ? ntp * sizeof(XplorEntry<S>) : 0) + 32;
+        return PairTable<E, S>::bytes(ntp) + (XPLOR ? ntp * sizeof(XplorEntry<S>) : 0) + 32
+               + (SPLIT ? AcceptQueue::bytes(block) : 0);
         }
 
     AZP_D XplorEntry<S>& xplor(unsigned int t) const
@@ -411,6 +536,8 @@ template<class E_, class S_, bool XPLOR, bool VIRIAL, int NTM_> struct IsoFamily
         PairTable<E, S>& tab = types.tab;
         tab.carve(ntp);
         xplor_off = (tab.end_off(ntp) + 15u) & ~15u;
+        unsigned int split_off = xplor_off; // SPLIT excludes XPLOR: the queue takes the table's place
+        carve_split(split, split_off);
         for (unsigned int t = threadIdx.x; t < ntp; t += blockDim.x)
             {
             const S rc = a.rcutsq[t];
@@ -437,6 +564,7 @@ template<class E_, class S_, bool XPLOR, bool VIRIAL, int NTM_> struct IsoFamily
     AZP_D void begin_row(const KernelArgs<S>& a, unsigned int, unsigned int ti)
         {
         types.begin_row(ti, a.ntypes);
+        split.begin_row(types);
         }
 
     // What is left of a neighbour once its gathered position has been consumed: the pipelined
@@ -447,30 +575,70 @@ template<class E_, class S_, bool XPLOR, bool VIRIAL, int NTM_> struct IsoFamily
         S dx, dy, dz;
         unsigned int tj;
         };
-    AZP_D Head head(const KernelArgs<S>& a, const RowGeometry<S>& g, unsigned int, const Vec4<S>& pj) const
+    AZP_D Head head(const KernelArgs<S>& a, const RowGeometry<S>& g, unsigned int j, const Vec4<S>& pj)
         {
         Head h;
         g.displacement(a.box, pj, h.dx, h.dy, h.dz);
         h.tj = NTM == 1 ? 0u : scalar_as_uint(pj.w);
+        if (SPLIT && split.rare(h.tj))
+            push_split(split, j); // evaluated by drain_one() once the row is done
         return h;
         }
-    template<bool WRAP> AZP_D Head head_t(const KernelArgs<S>& a, const RowGeometry<S>& g, const Vec4<S>& pj) const
+    template<bool WRAP> AZP_D Head head_t(const KernelArgs<S>& a, const RowGeometry<S>& g, unsigned int j, const Vec4<S>& pj)
         {
         Head h;
         g.template displacement_t<WRAP>(a.box, pj, h.dx, h.dy, h.dz);
         h.tj = NTM == 1 ? 0u : scalar_as_uint(pj.w);
+        if (SPLIT && split.rare(h.tj))
+            push_split(split, j);
         return h;
         }
     AZP_D void pair(const KernelArgs<S>& a, const RowGeometry<S>& g, unsigned int j, const Vec4<S>& pj)
         {
         body(a, head(a, g, j, pj));
+        if (SPLIT)
+            drain_if_short(a, g, 1u);
+        }
+    // FormSplit: evaluate the queued rare-form neighbours of this lane. Lanes of a warp that hold
+    // entries run the loop together; a lane's queue cannot overflow because process_row drains
+    // whenever fewer than a trip's worth of slots is left.
+    AZP_D void drain_if_short(const KernelArgs<S>& a, const RowGeometry<S>& g, unsigned int room)
+        {
+        if (split_short(split, room))
+            drain(a, g);
+        }
+    AZP_D void drain(const KernelArgs<S>& a, const RowGeometry<S>& g)
+        {
+        while (split_pending(split))
+            {
+            const unsigned int j = pop_split(split);
+            const Vec4<S> pj = load4(a.pos, j);
+            Head h;
+            g.displacement(a.box, pj, h.dx, h.dy, h.dz);
+            h.tj = scalar_as_uint(pj.w);
+            evaluate<false, true>(h);
+            }
+        }
+    // a row whose live partners are all deferred still has to be streamed
+    AZP_D bool row_off() const
+        {
+        return types.row_disabled() && !split.any();
         }
     AZP_D void body(const KernelArgs<S>&, const Head& h)
         {
+        evaluate<SPLIT, false>(h);
+        }
+    // INPLACE_OF_SPLIT: the in-place evaluation of a family with rare-form deferral (rare
+    // neighbours arrive with rcutsq = 0): only the forms below E::kHeavyForm are compiled in
+    // TABLE: constants from the shared-memory table (the drain of a split row, whose register
+    // copies hold the in-place constants) instead of the row's register copies
+    template<bool INPLACE_OF_SPLIT, bool TABLE> AZP_D void evaluate(const Head& h)
+        {
         const S dx = h.dx, dy = h.dy, dz = h.dz;
         const unsigned int tj = h.tj;
+        const unsigned int t_tab = TABLE ? index2d(2u, types.ti & 1u, tj & 1u) : 0u;
         const S rsq = fma(dz, dz, fma(dy, dy, dx * dx));
-        const S rcutsq = types.rcutsq(tj);
+        const S rcutsq = TABLE ? types.tab.rcutsq(t_tab) : types.rcutsq(tj);
         const bool inside = rsq < rcutsq;
         S force_divr = S(0), pair_eng = S(0);
         if (XPLOR)
@@ -506,10 +674,10 @@ template<class E_, class S_, bool XPLOR, bool VIRIAL, int NTM_> struct IsoFamily
             // which the cheap dense-fluid potentials, PLJ and Yukawa, do not get back).
             if (E::kWarpVote && __ballot_sync(__activemask(), inside) == 0u)
                 return;
-            const Cache c = types.cache(tj);
+            const Cache c = TABLE ? types.tab.cache(t_tab) : types.cache(tj);
             S f = S(0), e = S(0);
             E eval(rsq, rcutsq, c);
-            eval.evalPair(f, e, false);
+            eval_in_place<INPLACE_OF_SPLIT>(eval, f, e);
             force_divr = inside ? f : S(0);
             pair_eng = inside ? e : S(0);
             }
@@ -572,6 +740,7 @@ template<class EA, class EB, class S_, bool VIRIAL, int NTM_> struct FusedIsoFam
     static constexpr int PIPE = 2;
     static constexpr bool QUEUE = false;
     static constexpr bool MULTIROW = false;
+    static constexpr bool SPLIT = false;
 
     TypeLookup<EA, S, NTM> types; // potential A (row_kernel reads rc_max through it: see stage)
     TypeLookup<EB, S, NTM> types_b;
@@ -635,7 +804,7 @@ template<class EA, class EB, class S_, bool VIRIAL, int NTM_> struct FusedIsoFam
         h.tj = NTM == 1 ? 0u : scalar_as_uint(pj.w);
         return h;
         }
-    template<bool WRAP> AZP_D Head head_t(const KernelArgs<S>& a, const RowGeometry<S>& g, const Vec4<S>& pj) const
+    template<bool WRAP> AZP_D Head head_t(const KernelArgs<S>& a, const RowGeometry<S>& g, unsigned int, const Vec4<S>& pj) const
         {
         Head h;
         g.template displacement_t<WRAP>(a.box, pj, h.dx, h.dy, h.dz);
@@ -733,6 +902,7 @@ template<class E_, class S_, bool VIRIAL, int NTM_> struct DpdFamily
     static constexpr int PIPE = 0;
     static constexpr bool QUEUE = true;
     static constexpr bool MULTIROW = AZP_ROWS_PER_GROUP > 1;
+    static constexpr bool SPLIT = false;
 
     TypeLookup<E, S, NTM> types;
     AcceptQueue queue;
@@ -912,6 +1082,7 @@ template<class E_, class S_, bool VIRIAL, int NTM_> struct AnisoFamily
 #endif
     static constexpr bool QUEUE = AZP_ANISO_QUEUE != 0;
     static constexpr bool MULTIROW = AZP_ROWS_PER_GROUP > 1;
+    static constexpr bool SPLIT = false;
 
     TypeLookup<E, S, NTM> types;
     AcceptQueue queue;
@@ -1099,6 +1270,10 @@ template<class Fam> AZP_D auto row_disabled_dispatch(const Fam& fam) -> decltype
     {
     return fam.types.row_disabled() && fam.types_b.row_disabled();
     }
+template<class Fam> AZP_D auto row_disabled_dispatch(const Fam& fam) -> decltype(fam.row_off())
+    {
+    return fam.row_off();
+    }
 template<class Fam, class... X> AZP_D bool row_disabled_dispatch(const Fam& fam, X...)
     {
     return fam.types.row_disabled();
@@ -1116,16 +1291,16 @@ AZP_D auto head_dispatch(Fam&, const KernelArgs<S>&, const RowGeometry<S>&, unsi
     return NoHead();
     }
 template<bool WRAP, class Fam, class S, class H>
-AZP_D auto heads_dispatch(Fam& fam, const KernelArgs<S>& a, const RowGeometry<S>& g, const Vec4<S>& p0, const Vec4<S>& p1,
+AZP_D auto heads_dispatch(Fam& fam, const KernelArgs<S>& a, const RowGeometry<S>& g, const uint4& j, const Vec4<S>& p0, const Vec4<S>& p1,
                           const Vec4<S>& p2, const Vec4<S>& p3, H& h0, H& h1, H& h2, H& h3) -> typename std::enable_if<Fam::PIPE == 2>::type
     {
-    h0 = fam.template head_t<WRAP>(a, g, p0);
-    h1 = fam.template head_t<WRAP>(a, g, p1);
-    h2 = fam.template head_t<WRAP>(a, g, p2);
-    h3 = fam.template head_t<WRAP>(a, g, p3);
+    h0 = fam.template head_t<WRAP>(a, g, j.x, p0);
+    h1 = fam.template head_t<WRAP>(a, g, j.y, p1);
+    h2 = fam.template head_t<WRAP>(a, g, j.z, p2);
+    h3 = fam.template head_t<WRAP>(a, g, j.w, p3);
     }
 template<bool WRAP, class Fam, class S, class H>
-AZP_D auto heads_dispatch(Fam&, const KernelArgs<S>&, const RowGeometry<S>&, const Vec4<S>&, const Vec4<S>&, const Vec4<S>&,
+AZP_D auto heads_dispatch(Fam&, const KernelArgs<S>&, const RowGeometry<S>&, const uint4&, const Vec4<S>&, const Vec4<S>&, const Vec4<S>&,
                           const Vec4<S>&, H&, H&, H&, H&) -> typename std::enable_if<Fam::PIPE != 2>::type
     {
     }
@@ -1173,6 +1348,27 @@ template<class Fam> AZP_D auto queue_pending(const Fam& fam) -> typename std::en
 template<class Fam> AZP_D auto queue_pending(const Fam&) -> typename std::enable_if<!Fam::QUEUE, bool>::type
     {
     return false;
+    }
+
+// rare-form deferral (FormSplit) of the isotropic family: drain when a trip could overflow the
+// lane's queue, and when the row is done
+template<class Fam, class S>
+AZP_D auto split_trip_dispatch(Fam& fam, const KernelArgs<S>& a, const RowGeometry<S>& g) -> typename std::enable_if<Fam::SPLIT>::type
+    {
+    fam.drain_if_short(a, g, AcceptQueue::ROOM);
+    }
+template<class Fam, class S>
+AZP_D auto split_trip_dispatch(Fam&, const KernelArgs<S>&, const RowGeometry<S>&) -> typename std::enable_if<!Fam::SPLIT>::type
+    {
+    }
+template<class Fam, class S>
+AZP_D auto split_finish_dispatch(Fam& fam, const KernelArgs<S>& a, const RowGeometry<S>& g) -> typename std::enable_if<Fam::SPLIT>::type
+    {
+    fam.drain(a, g);
+    }
+template<class Fam, class S>
+AZP_D auto split_finish_dispatch(Fam&, const KernelArgs<S>&, const RowGeometry<S>&) -> typename std::enable_if<!Fam::SPLIT>::type
+    {
     }
 
 // One row for one group of `tpp` lanes: geometry, neighbour stream, reduction, store.
@@ -1233,56 +1429,67 @@ AZP_D void process_row(Fam& fam,
     unsigned int v = v_begin + lane;
     if (Fam::PIPE == 2)
         {
+        // pointer + countdown form: the loop carries one 64-bit cursor and one trip counter
+        // (instead of v, v_end and the lane stride, which ptxas re-derived every trip)
+        const uint4* cur4 = base4 + v;
+        unsigned int trips = v < v_end ? (v_end - v + tpp - 1u) / tpp : 0u;
         uint4 j_cur = make_uint4(0u, 0u, 0u, 0u), j_nxt = make_uint4(0u, 0u, 0u, 0u);
         Vec4<S> p0, p1, p2, p3;
-        if (v < v_end)
+        if (trips > 0u)
             {
-            j_cur = __ldg(base4 + v);
+            j_cur = load_index4(cur4);
             p0 = load4(a.pos, j_cur.x);
             p1 = load4(a.pos, j_cur.y);
             p2 = load4(a.pos, j_cur.z);
             p3 = load4(a.pos, j_cur.w);
-            if (v + tpp < v_end)
-                j_nxt = __ldg(base4 + v + tpp);
+            if (trips > 1u)
+                j_nxt = load_index4(cur4 + tpp);
             }
-        while (v < v_end)
+        while (trips > 0u)
             {
-            const unsigned int v1 = v + tpp, v2 = v1 + tpp;
 #if AZP_TRIP_WRAP
             // one (warp-uniform) skip_wrap branch per trip instead of one per neighbour
             decltype(head_dispatch(fam, a, g, 0u, p0)) h0, h1, h2, h3;
             if (g.skip_wrap)
-                heads_dispatch<false>(fam, a, g, p0, p1, p2, p3, h0, h1, h2, h3);
+                heads_dispatch<false>(fam, a, g, j_cur, p0, p1, p2, p3, h0, h1, h2, h3);
             else
-                heads_dispatch<true>(fam, a, g, p0, p1, p2, p3, h0, h1, h2, h3);
+                heads_dispatch<true>(fam, a, g, j_cur, p0, p1, p2, p3, h0, h1, h2, h3);
 #else
             const auto h0 = head_dispatch(fam, a, g, j_cur.x, p0);
             const auto h1 = head_dispatch(fam, a, g, j_cur.y, p1);
             const auto h2 = head_dispatch(fam, a, g, j_cur.z, p2);
             const auto h3 = head_dispatch(fam, a, g, j_cur.w, p3);
 #endif
-            if (v1 < v_end)
+            if (trips > 1u)
                 {
                 j_cur = j_nxt;
                 p0 = load4(a.pos, j_cur.x);
                 p1 = load4(a.pos, j_cur.y);
                 p2 = load4(a.pos, j_cur.z);
                 p3 = load4(a.pos, j_cur.w);
-                if (v2 < v_end)
-                    j_nxt = __ldg(base4 + v2);
+                if (trips > 2u)
+                    j_nxt = load_index4(cur4 + 2u * tpp);
                 }
             body_dispatch(fam, a, h0);
             body_dispatch(fam, a, h1);
             body_dispatch(fam, a, h2);
             body_dispatch(fam, a, h3);
-            v = v1;
+            split_trip_dispatch(fam, a, g);
+#if AZP_NLIST_LINE_PREFETCH
+            // at the start of a 128-byte line of the row: request the line AZP_NLIST_LINE_PREFETCH
+            // lines ahead (one lane-private request per 8 trips)
+            if ((reinterpret_cast<uintptr_t>(cur4) & 127u) == 0u && trips > 8u * AZP_NLIST_LINE_PREFETCH)
+                prefetch_l2(cur4 + 8u * AZP_NLIST_LINE_PREFETCH);
+#endif
+            cur4 += tpp;
+            --trips;
             }
         }
     else if (!Fam::QUEUE)
         {
         for (; v < v_end; v += tpp)
             {
-            const uint4 j = __ldg(base4 + v);
+            const uint4 j = load_index4(base4 + v);
             const Vec4<S> q0 = load4(a.pos, j.x);
             const Vec4<S> q1 = load4(a.pos, j.y);
             const Vec4<S> q2 = load4(a.pos, j.z);
@@ -1291,6 +1498,7 @@ AZP_D void process_row(Fam& fam,
             pair_dispatch(fam, a, g, j.y, q1);
             pair_dispatch(fam, a, g, j.z, q2);
             pair_dispatch(fam, a, g, j.w, q3);
+            split_trip_dispatch(fam, a, g);
             }
         }
 
@@ -1322,14 +1530,14 @@ AZP_D void process_row(Fam& fam,
         // position gathers across the heavy rounds as well costs 96 registers and 24 %.)
         uint4 j_nxt = make_uint4(0u, 0u, 0u, 0u);
         if (more)
-            j_nxt = __ldg(base4 + v);
+            j_nxt = load_index4(base4 + v);
         while (__any_sync(full, more))
             {
             if (more)
                 {
                 const uint4 j = j_nxt;
                 if (v + tpp < v_end)
-                    j_nxt = __ldg(base4 + v + tpp);
+                    j_nxt = load_index4(base4 + v + tpp);
                 const Vec4<S> q0 = load4(a.pos, j.x);
                 const Vec4<S> q1 = load4(a.pos, j.y);
                 const Vec4<S> q2 = load4(a.pos, j.z);
@@ -1362,6 +1570,7 @@ AZP_D void process_row(Fam& fam,
             heavy_dispatch(fam, a, g);
         }
 
+    split_finish_dispatch(fam, a, g);
     fam.finish(a, row, active && lane == 0, tpp);
     }
 
@@ -1372,23 +1581,27 @@ AZP_D void process_row(Fam& fam,
 // rows. LONGPASS = true: the second pass, launched with tpp = 32 on a fixed grid; every warp
 // takes queued rows until the queue is empty. If the queue overflows, the main pass evaluates
 // the row in place, so correctness never depends on the queue capacity.
-template<class Fam, bool LONGPASS>
+// ONE_LANE: the main pass compiled for threads_per_particle = 1 (the launch shape of every dense
+// configuration): the lane stride of the neighbour loop, the shuffle reductions and the group
+// broadcasts fold away at compile time instead of being re-derived from tpp_log2 every trip.
+template<class Fam, bool LONGPASS, bool ONE_LANE = false>
 __global__ void __launch_bounds__(max_block<typename Fam::S>())
     row_kernel(const __grid_constant__ KernelArgs<typename Fam::S> a,
                const typename Fam::E::param_type* __restrict__ params,
-               const unsigned int tpp_log2)
+               const unsigned int tpp_log2_arg)
     {
     const unsigned int ntp = Fam::NTM == 1 ? 1u : a.ntypes * a.ntypes;
     Fam fam;
     fam.stage(a, params, ntp);
 
-    const unsigned int tpp = 1u << tpp_log2;
+    const unsigned int tpp_log2 = ONE_LANE ? 0u : tpp_log2_arg;
+    const unsigned int tpp = ONE_LANE ? 1u : (1u << tpp_log2);
     const unsigned int gtid = blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned int lane = gtid & (tpp - 1u);
+    const unsigned int lane = ONE_LANE ? 0u : (gtid & (tpp - 1u));
     if (!LONGPASS && !Fam::MULTIROW)
         {
         // one row per group of tpp lanes (the launch layer sizes the grid accordingly)
-        const unsigned int slot = gtid >> tpp_log2;
+        const unsigned int slot = ONE_LANE ? gtid : (gtid >> tpp_log2);
         const unsigned int nslots = a.row_ids ? a.n_row_ids : a.N;
         bool active = slot < nslots;
         unsigned int row = 0, n = 0;

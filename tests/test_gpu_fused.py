@@ -1,6 +1,9 @@
 """GPU: the fused two-potential pass (``azp_pair_forces_fused_*``):
-Colloid + Hertz over one sweep of the list give, bit for bit, the outputs of the two separate
-launches -- including the colloid rows that go through the warp-per-row long pass."""
+Colloid + Hertz over one sweep of the list give the outputs of the two separate launches --
+including the colloid rows that go through the warp-per-row long pass. Hertz is bit-identical;
+Colloid to the order of summation: its separate launch defers the rare sphere-point /
+sphere-sphere pairs of a row behind the common ones (pair_kernels.cuh, FormSplit), the fused
+pass evaluates every pair in list order."""
 
 import numpy as np
 import pytest
@@ -21,6 +24,13 @@ def test_fused_colloid_hertz_equals_separate_launches(dtype, virial):
     state = wl.make_state(dtype=dtype)
     nl = az.nlist.Cell(buffer=synth.BUFFER)
     colloid, hertz = wl.make_potentials(nl)
+    tol = 2e-6 if dtype == np.float32 else 1e-14
+
+    def same(pot, got, want):
+        if pot is hertz:
+            return torch.equal(got, want)
+        return float((got - want).abs().max()) <= tol * float(want.abs().max())
+
     for mode_c, mode_h in (("none", "none"), ("shift", "none")):
         colloid.mode, hertz.mode = mode_c, mode_h
         for shape in ((128, 1), (128, 4), (64, 32)):
@@ -37,16 +47,16 @@ def test_fused_colloid_hertz_equals_separate_launches(dtype, virial):
             fused.kernel_parameters = shape
             fused.compute(compute_virial=virial)
             for p, (f, w) in zip((colloid, hertz), want):
-                assert torch.equal(p._force, f), (type(p).__name__, shape, mode_c)
+                assert same(p, p._force, f), (type(p).__name__, shape, mode_c)
                 if virial:
-                    assert torch.equal(p._virial, w), (type(p).__name__, shape, mode_c)
+                    assert same(p, p._virial, w), (type(p).__name__, shape, mode_c)
     # a row range (what compute_to_host and the slice scheduler use)
     lo, hi = 1000, 50000
     for p in (colloid, hertz):
         p._force.fill_(3.0)
     fused.compute(compute_virial=virial, rows=(lo, hi))
     for p, (f, w) in zip((colloid, hertz), want):
-        assert torch.equal(p._force[lo:hi], f[lo:hi])
+        assert same(p, p._force[lo:hi], f[lo:hi])
         assert bool((p._force[:lo] == 3.0).all()) and bool((p._force[hi:] == 3.0).all())
 
 
