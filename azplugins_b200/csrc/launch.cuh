@@ -202,10 +202,12 @@ inline cudaError_t launch_rows(KernelArgs<typename Fam::S> k, const void* d_para
     if (s.tpp_log2 == 0)
         {
         auto kernel = row_kernel<Fam, false, true>;
-        err = ensure_smem(kernel, smem);
+        // the staged neighbour-list ring (ListStage) sits behind the family's own tables
+        const size_t smem1 = smem + ((AZP_STAGE_LIST != 0 && Fam::PIPE == 2) ? ListStage::bytes(s.block) : 0);
+        err = ensure_smem(kernel, smem1);
         if (err != cudaSuccess)
             return err;
-        kernel<<<s.grid, s.block, smem, stream>>>(k, params, 0u);
+        kernel<<<s.grid, s.block, smem1, stream>>>(k, params, 0u);
         }
     else
 #endif

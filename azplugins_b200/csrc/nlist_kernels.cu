@@ -347,12 +347,13 @@ template<class S, bool FILL> static int rows(const azp_nlist_args* a, cudaStream
     const NlistArgs<S> k = convert<S>(*a);
     if ((unsigned long long)k.row_offset + k.n_rows > a->N)
         return (int)cudaErrorInvalidValue;
-    // lanes per row from the mean cell population (candidates per stencil cell): a cell is
-    // swept TPP candidates at a time
-    const double per_cell = double(a->N) / (double(a->cell_dim[0]) * a->cell_dim[1] * a->cell_dim[2]);
+    // lanes per row (a cell is swept TPP candidates at a time). Measured on B200 (C2, 30
+    // candidates per cell, N = 1 M, rebuild reusing the capacities): 2 lanes 2.9 ms, 4 lanes 3.0,
+    // 16 lanes 4.8, 32 lanes 5.2 -- the sweep is instruction bound, so the fewest lanes that
+    // still coalesce pairs of 16-byte candidate loads win
     unsigned int tpp = a->threads_per_row;
     if (tpp == 0)
-        tpp = per_cell > 24.0 ? 16u : (per_cell > 6.0 ? 8u : 4u);
+        tpp = 2u;
     switch (tpp)
         {
     case 1:

@@ -53,6 +53,12 @@
 #ifndef AZP_NLIST_LINE_PREFETCH
 #define AZP_NLIST_LINE_PREFETCH 0
 #endif
+// Neighbour-list staging of the one-lane-per-row pipelined loop (ListStage below): 0 = off (each
+// lane loads its row 16 bytes per trip through L1), 1 = TMA bulk copies (cp.async.bulk +
+// mbarrier), 2 = cp.async (LDGSTS) 16-byte copies
+#ifndef AZP_STAGE_LIST
+#define AZP_STAGE_LIST 0
+#endif
 
 namespace azp
     {
@@ -288,6 +294,104 @@ struct AcceptQueue
         {
         --n;
         return reinterpret_cast<const unsigned int*>(azp_smem + off)[n * blockDim.x + threadIdx.x];
+        }
+    };
+
+// Staging of the neighbour-list stream through shared memory (AZP_STAGE_LIST). With one lane per
+// row a lane's 16-byte index load is a fresh HBM miss every other trip, and the bytes a warp
+// keeps in flight (32 x 16) bound the stream by latency. Here every lane copies
+// the next CH index vectors of ITS OWN row into a private slot of a two-stage ring --
+// asynchronously, without registers: as one TMA bulk copy (cp.async.bulk, completion on the
+// warp's mbarrier of that stage) or as CH cp.async copies -- two chunks (8 trips) ahead of the
+// math, and reads the indices of a trip back with one LDS.128. Slots are PITCH = 16 CH + 16
+// bytes apart, so the 32 lanes of a warp read 32 different bank groups (20 words mod 32 walks
+// the multiples of 4). No lane ever reads another lane's slot: no cross-lane exchange of row
+// pointers, and the cp.async variant needs no barrier at all. Only full vectors inside the row
+// are staged; the partial vectors at the row ends keep their guarded scalar path.
+struct ListStage
+    {
+    static constexpr unsigned int CH = 4;                 // index vectors per row and chunk
+    static constexpr unsigned int PITCH = 16u * CH + 16u; // bytes per row slot
+    static constexpr unsigned int STAGES = 2;
+    static constexpr unsigned int WARP_BYTES = STAGES * 32u * PITCH;
+    unsigned int slots; // byte offset (azp_smem) of this lane's slot of stage 0
+    unsigned int bars;  // byte offset of this warp's mbarriers (one per stage)
+
+    AZP_HD static size_t bytes(size_t block)
+        {
+        return (block / 32u) * (WARP_BYTES + 8u * STAGES) + 128u;
+        }
+    // `off`: first free byte of the dynamic shared memory
+    AZP_D void carve(unsigned int off)
+        {
+        const unsigned int warp = threadIdx.x >> 5, lane = threadIdx.x & 31u, nwarps = blockDim.x >> 5;
+        const unsigned int base = (off + 127u) & ~127u;
+        slots = base + warp * WARP_BYTES + lane * PITCH;
+        bars = base + nwarps * WARP_BYTES + warp * 8u * STAGES;
+        }
+    AZP_D unsigned int slot(unsigned int stage) const
+        {
+        return slots + stage * 32u * PITCH;
+        }
+    static AZP_D unsigned int shared_addr(unsigned int off)
+        {
+        return (unsigned int)__cvta_generic_to_shared(azp_smem + off);
+        }
+    AZP_D void init() const
+        {
+#if AZP_STAGE_LIST == 1
+        if ((threadIdx.x & 31u) == 0u)
+            for (unsigned int st = 0; st < STAGES; ++st)
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], 32;" ::"r"(shared_addr(bars + 8u * st)) : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+#endif
+        }
+    // copy vectors [first, first + count) of the lane's row (count <= CH) into its slot of `stage`
+    AZP_D void issue(unsigned int stage, const uint4* src, unsigned int count) const
+        {
+#if AZP_STAGE_LIST == 1
+        const unsigned int bar = shared_addr(bars + 8u * stage);
+        if (count > 0u)
+            {
+            const unsigned int nbytes = 16u * count;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nbytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(shared_addr(slot(stage))),
+                         "l"(src), "r"(nbytes), "r"(bar)
+                         : "memory");
+            }
+        else
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+#else
+        const unsigned int dst = shared_addr(slot(stage));
+#pragma unroll
+        for (unsigned int c = 0; c < CH; ++c)
+            if (c < count)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * c), "l"(src + c) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+        }
+    // chunk `k` has landed (chunks are issued in order, at most one younger chunk is in flight)
+    AZP_D void wait(unsigned int k) const
+        {
+#if AZP_STAGE_LIST == 1
+        const unsigned int bar = shared_addr(bars + 8u * (k % STAGES));
+        const unsigned int parity = (k / STAGES) & 1u;
+        asm volatile("{\n"
+                     ".reg .pred p;\n"
+                     "AZP_STAGE_WAIT:\n"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                     "@!p bra AZP_STAGE_WAIT;\n"
+                     "}" ::"r"(bar),
+                     "r"(parity)
+                     : "memory");
+#else
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+#endif
+        }
+    AZP_D uint4 read(unsigned int stage, unsigned int t) const
+        {
+        return *reinterpret_cast<const uint4*>(azp_smem + slot(stage) + 16u * t);
         }
     };
 
@@ -1011,6 +1115,12 @@ template<class E_, class S_, bool VIRIAL, int NTM_> struct DpdFamily
         }
     AZP_D void heavy(const KernelArgs<S>& a, const RowGeometry<S>& g)
         {
+#ifdef AZP_DIAG_NO_HEAVY
+        // timing diagnosis only (wrong forces): what does the scan + list stream cost alone?
+        if (queue.n > 0u)
+            fx += __uint_as_float(queue.pop());
+        return;
+#endif
         const unsigned int pending = queue.n;
         if (pending > 0u)
             {
@@ -1160,6 +1270,10 @@ template<class E_, class S_, bool VIRIAL, int NTM_> struct AnisoFamily
         const S rcutsq = types.rcutsq(tj);
         if (rsq <= rcutsq)
             {
+#ifdef AZP_DIAG_NO_HEAVY
+            fx += dr.x; // timing diagnosis only (wrong forces)
+            return;
+#endif
             const Cache c = types.cache(tj);
             accept(a, c, j, rsq, rcutsq, dr);
             }
@@ -1372,7 +1486,7 @@ AZP_D auto split_finish_dispatch(Fam&, const KernelArgs<S>&, const RowGeometry<S
     }
 
 // One row for one group of `tpp` lanes: geometry, neighbour stream, reduction, store.
-template<class Fam>
+template<class Fam, bool STAGED = false>
 AZP_D void process_row(Fam& fam,
                        const KernelArgs<typename Fam::S>& a,
                        const unsigned int ntp,
@@ -1381,7 +1495,8 @@ AZP_D void process_row(Fam& fam,
                        const uint64_t head,
                        const bool active,
                        const unsigned int lane,
-                       const unsigned int tpp)
+                       const unsigned int tpp,
+                       const ListStage* ls = nullptr)
     {
     typedef typename Fam::S S;
     const unsigned int i = active ? row + a.row_offset : 0u;
@@ -1427,7 +1542,83 @@ AZP_D void process_row(Fam& fam,
     // with the smallest register footprint -- best for the heavy DPD / anisotropic evaluators,
     // which hide latency with occupancy instead (measured).
     unsigned int v = v_begin + lane;
-    if (Fam::PIPE == 2)
+    if (Fam::PIPE == 2 && STAGED)
+        {
+        // One lane per row, neighbour list staged through shared memory (ListStage). The loop is
+        // warp-uniform: it runs for the longest row of the warp, lanes whose row is done idle.
+        // Trip T consumes the positions gathered during trip T - 1, reads the indices of trip
+        // T + 1 from the ring, gathers, then runs the bodies; when T + 1 enters a new chunk the
+        // chunk behind it has been consumed and its stage is refilled two chunks ahead.
+        constexpr unsigned int CH = ListStage::CH;
+        const unsigned int full = 0xffffffffu;
+        const unsigned int nvec = v_begin < v_end ? v_end - v_begin : 0u;
+        const unsigned int nvec_max = __reduce_max_sync(full, nvec);
+        const uint4* src = base4 + v_begin;
+        auto count_of = [&](unsigned int k) -> unsigned int
+            {
+            const unsigned int first = CH * k;
+            return nvec > first ? min(CH, nvec - first) : 0u;
+            };
+        uint4 j_cur = make_uint4(0u, 0u, 0u, 0u);
+        Vec4<S> p0, p1, p2, p3;
+        if (nvec_max > 0u)
+            {
+            ls->issue(0u, src, count_of(0u));
+            ls->issue(1u, src + CH, count_of(1u));
+            ls->wait(0u);
+            if (nvec > 0u)
+                {
+                j_cur = ls->read(0u, 0u);
+                p0 = load4(a.pos, j_cur.x);
+                p1 = load4(a.pos, j_cur.y);
+                p2 = load4(a.pos, j_cur.z);
+                p3 = load4(a.pos, j_cur.w);
+                }
+            }
+        for (unsigned int T = 0; T < nvec_max; ++T)
+            {
+            const bool act = T < nvec;
+            decltype(head_dispatch(fam, a, g, 0u, p0)) h0, h1, h2, h3;
+            if (act)
+                {
+                h0 = head_dispatch(fam, a, g, j_cur.x, p0);
+                h1 = head_dispatch(fam, a, g, j_cur.y, p1);
+                h2 = head_dispatch(fam, a, g, j_cur.z, p2);
+                h3 = head_dispatch(fam, a, g, j_cur.w, p3);
+                }
+            const unsigned int Tn = T + 1u;
+            const unsigned int kn = Tn / CH, tn = Tn % CH;
+            if (tn == 0u && Tn < nvec_max)
+                ls->wait(kn); // warp-uniform
+            if (Tn < nvec)
+                {
+                j_cur = ls->read(kn % ListStage::STAGES, tn);
+                p0 = load4(a.pos, j_cur.x);
+                p1 = load4(a.pos, j_cur.y);
+                p2 = load4(a.pos, j_cur.z);
+                p3 = load4(a.pos, j_cur.w);
+                }
+            if (tn == 0u && Tn < nvec_max)
+                {
+                // chunk kn - 1 is consumed (its last indices were read one trip ago): refill its
+                // stage with chunk kn + 1
+                __syncwarp();
+                ls->issue((kn + 1u) % ListStage::STAGES, src + CH * (kn + 1u), count_of(kn + 1u));
+                }
+            if (act)
+                {
+                body_dispatch(fam, a, h0);
+                body_dispatch(fam, a, h1);
+                body_dispatch(fam, a, h2);
+                body_dispatch(fam, a, h3);
+                split_trip_dispatch(fam, a, g);
+                }
+            }
+#if AZP_STAGE_LIST == 2
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
+        }
+    else if (Fam::PIPE == 2)
         {
         // pointer + countdown form: the loop carries one 64-bit cursor and one trip counter
         // (instead of v, v_end and the lane stride, which ptxas re-derived every trip)
@@ -1630,7 +1821,16 @@ __global__ void __launch_bounds__(max_block<typename Fam::S>())
                     }
                 }
             }
-        process_row(fam, a, ntp, row, n, head, active, lane, tpp);
+        constexpr bool STAGED = AZP_STAGE_LIST != 0 && ONE_LANE && Fam::PIPE == 2;
+        if (STAGED)
+            {
+            ListStage ls;
+            ls.carve((unsigned int)Fam::smem_bytes(ntp, blockDim.x));
+            ls.init();
+            process_row<Fam, STAGED>(fam, a, ntp, row, n, head, active, lane, tpp, &ls);
+            }
+        else
+            process_row<Fam, false>(fam, a, ntp, row, n, head, active, lane, tpp);
         }
     else if (!LONGPASS)
         {
