@@ -118,8 +118,20 @@ template<class S> __global__ void nlist_sorted_positions(const NlistArgs<S> a)
 // the tilt factors) with that image number instead of rint(d / L). For every pair closer than
 // r_list (<= cell width <= L / 3) the two agree bit for bit; farther candidates fail the cutoff
 // either way. An axis with a single cell (box shorter than 3 r_list) keeps rint().
-template<class S, bool FILL, unsigned int TPP> __global__ void __launch_bounds__(128) nlist_rows(const NlistArgs<S> a)
+// ORTHO: no tilt factors and at least three cells on every periodic axis -- the image update
+// collapses to one multiply-add per axis with the image number of the stencil cell (identical
+// bits: the tilt terms of the general sequence subtract exact zeros).
+template<class S, bool FILL, unsigned int TPP, bool ORTHO> __global__ void __launch_bounds__(128) nlist_rows(const NlistArgs<S> a)
     {
+    // squared list cutoffs of the type pairs (<= 8 types) staged in shared memory
+    __shared__ S s_rlistsq[64];
+    const bool small_table = a.ntypes <= 8u;
+    if (small_table)
+        {
+        for (unsigned int t = threadIdx.x; t < a.ntypes * a.ntypes; t += blockDim.x)
+            s_rlistsq[t] = a.rlistsq[t];
+        __syncthreads();
+        }
     const unsigned int gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned int lane = gtid & (TPP - 1u);
     const unsigned int r = gtid / TPP;
@@ -181,7 +193,15 @@ template<class S, bool FILL, unsigned int TPP> __global__ void __launch_bounds__
                         {
                         const Vec4<S> pj = load4(a.cell_pos, s);
                         S x = pi.x - pj.x, y = pi.y - pj.y, z = pi.z - pj.z;
+                        if (ORTHO)
+                            {
+                            x -= b.L[0] * imgx;
+                            y -= b.L[1] * imgy;
+                            z -= b.L[2] * imgz;
+                            }
                         // BoxDim::minImage's sequence with the image numbers of this cell
+                        else
+                            {
                         if (b.periodic[2])
                             {
                             const S img = a.grid.reach[2] ? imgz : rint_small(z * b.Linv[2]);
@@ -200,9 +220,11 @@ template<class S, bool FILL, unsigned int TPP> __global__ void __launch_bounds__
                             const S img = a.grid.reach[0] ? imgx : rint_small(x * b.Linv[0]);
                             x -= b.L[0] * img;
                             }
+                            }
                         const S rsq = x * x + y * y + z * z;
                         const unsigned int tj = min(scalar_as_uint(pj.w), a.ntypes - 1u);
-                        if (rsq < a.rlistsq[index2d(a.ntypes, ti, tj)])
+                        const unsigned int tp = index2d(a.ntypes, ti, tj);
+                        if (rsq < (small_table ? s_rlistsq[tp] : a.rlistsq[tp]))
                             {
                             j = a.cell_order[s];
                             pass = j != i;
@@ -330,7 +352,16 @@ template<class S, bool FILL, unsigned int TPP> static int rows_tpp(const NlistAr
     {
     const unsigned int block = 128;
     const unsigned long long threads = (unsigned long long)k.n_rows * TPP;
-    nlist_rows<S, FILL, TPP><<<(unsigned int)((threads + block - 1) / block), block, 0, st>>>(k);
+    const unsigned int grid = (unsigned int)((threads + block - 1) / block);
+    // a non-periodic axis has image 0 for every stencil cell that is not skipped, and an axis
+    // with a single cell (reach 0) needs rint(): both keep the general sequence
+    bool ortho = k.box.xy == S(0) && k.box.xz == S(0) && k.box.yz == S(0);
+    for (int d = 0; d < 3; ++d)
+        ortho = ortho && k.box.periodic[d] && k.grid.reach[d] == 1;
+    if (ortho)
+        nlist_rows<S, FILL, TPP, true><<<grid, block, 0, st>>>(k);
+    else
+        nlist_rows<S, FILL, TPP, false><<<grid, block, 0, st>>>(k);
     return (int)cudaGetLastError();
     }
 

@@ -46,8 +46,13 @@
 #define AZP_TRIP_WRAP 0
 #endif
 // queued neighbours a lane evaluates per heavy round of the deferred-accept families (1 or 2)
+// (measured, C4 4 M / C5 4 M: DPD 1 -> 2: 0.685 -> 0.748 ms; two-patch Morse with the queue
+// 1 -> 2: 0.452 -> 0.439 ms, in-place evaluation 0.454 ms)
 #ifndef AZP_HEAVY_UNROLL
 #define AZP_HEAVY_UNROLL 1
+#endif
+#ifndef AZP_ANISO_HEAVY_UNROLL
+#define AZP_ANISO_HEAVY_UNROLL 2
 #endif
 // lines (128 B) ahead of a lane's cursor that the pipelined loop requests into L2; 0 = off
 #ifndef AZP_NLIST_LINE_PREFETCH
@@ -1184,11 +1189,12 @@ template<class E_, class S_, bool VIRIAL, int NTM_> struct AnisoFamily
     // registers here and is 50 % slower (0.69 vs 0.46 ms per 4 M particles) than hiding the
     // latency with occupancy (58 registers, 8 CTAs per SM)
     static constexpr int PIPE = 0;
-    // measured on C5 (51 % of the entries accepted, 16.6 per row): deferring the accepted pairs
-    // (AcceptQueue) saves 11 % of the instructions but lengthens the dependent memory chains and
-    // is 6 % slower, so the two-patch Morse family evaluates in place
+    // Deferred accept (AcceptQueue) for the two-patch Morse family. Round 1 measured it 6 %
+    // slower than evaluating in place (-11 % instructions, but one exposed gather latency per
+    // heavy round); with all gathers of a round issued together and two queued neighbours per
+    // lane and round it is 3.4 % faster (C5, 4 M particles: 0.454 -> 0.439 ms), so it is on.
 #ifndef AZP_ANISO_QUEUE
-#define AZP_ANISO_QUEUE 0
+#define AZP_ANISO_QUEUE 1
 #endif
     static constexpr bool QUEUE = AZP_ANISO_QUEUE != 0;
     static constexpr bool MULTIROW = AZP_ROWS_PER_GROUP > 1;
@@ -1304,18 +1310,18 @@ template<class E_, class S_, bool VIRIAL, int NTM_> struct AnisoFamily
         }
     AZP_D void heavy(const KernelArgs<S>& a, const RowGeometry<S>& g)
         {
-        // all gathers of the round (position + orientation of up to AZP_HEAVY_UNROLL queued
+        // all gathers of the round (position + orientation of up to AZP_ANISO_HEAVY_UNROLL queued
         // neighbours) are issued together: one exposed latency per round; the scan applied
         // pair()'s own cutoff test to the same displacement, so it is not repeated
         const unsigned int pending = queue.n;
         if (pending > 0u)
             {
             const unsigned int j0 = queue.pop();
-            const bool two = AZP_HEAVY_UNROLL > 1 && pending > 1u;
+            const bool two = AZP_ANISO_HEAVY_UNROLL > 1 && pending > 1u;
             const unsigned int j1 = two ? queue.pop() : j0;
             const Vec4<S> p0 = load4(a.pos, j0);
             const Vec4<S> q0 = load4(a.orientation, j0);
-            if (AZP_HEAVY_UNROLL > 1)
+            if (AZP_ANISO_HEAVY_UNROLL > 1)
                 {
                 const Vec4<S> p1 = load4(a.pos, j1);
                 const Vec4<S> q1 = load4(a.orientation, j1);
@@ -1546,27 +1552,25 @@ AZP_D void process_row(Fam& fam,
         {
         // One lane per row, neighbour list staged through shared memory (ListStage). The loop is
         // warp-uniform: it runs for the longest row of the warp, lanes whose row is done idle.
-        // Trip T consumes the positions gathered during trip T - 1, reads the indices of trip
-        // T + 1 from the ring, gathers, then runs the bodies; when T + 1 enters a new chunk the
-        // chunk behind it has been consumed and its stage is refilled two chunks ahead.
+        // It walks the chunks of CH index vectors; the CH trips of a chunk are unrolled, so the
+        // ring stage and the slot offsets are compile-time constants inside a trip. Trip t
+        // consumes the positions gathered during the previous trip, reads the indices of the
+        // next trip from the ring and gathers, then runs the bodies. The last trip of a chunk
+        // waits for the next chunk (issued two chunks = 2 CH trips earlier) and refills the
+        // stage it has just finished with the chunk after that.
         constexpr unsigned int CH = ListStage::CH;
         const unsigned int full = 0xffffffffu;
-        const unsigned int nvec = v_begin < v_end ? v_end - v_begin : 0u;
-        const unsigned int nvec_max = __reduce_max_sync(full, nvec);
-        const uint4* src = base4 + v_begin;
-        auto count_of = [&](unsigned int k) -> unsigned int
-            {
-            const unsigned int first = CH * k;
-            return nvec > first ? min(CH, nvec - first) : 0u;
-            };
+        unsigned int rem = v_begin < v_end ? v_end - v_begin : 0u; // vectors of this lane not yet consumed
+        const unsigned int nchunks = (__reduce_max_sync(full, rem) + CH - 1u) / CH;
+        const uint4* src = base4 + v_begin; // first vector of the chunk being consumed
         uint4 j_cur = make_uint4(0u, 0u, 0u, 0u);
         Vec4<S> p0, p1, p2, p3;
-        if (nvec_max > 0u)
+        if (nchunks > 0u)
             {
-            ls->issue(0u, src, count_of(0u));
-            ls->issue(1u, src + CH, count_of(1u));
+            ls->issue(0u, src, min(rem, CH));
+            ls->issue(1u, src + CH, rem > CH ? min(rem - CH, CH) : 0u);
             ls->wait(0u);
-            if (nvec > 0u)
+            if (rem > 0u)
                 {
                 j_cur = ls->read(0u, 0u);
                 p0 = load4(a.pos, j_cur.x);
@@ -1575,44 +1579,62 @@ AZP_D void process_row(Fam& fam,
                 p3 = load4(a.pos, j_cur.w);
                 }
             }
-        for (unsigned int T = 0; T < nvec_max; ++T)
+        for (unsigned int k = 0; k < nchunks; ++k)
             {
-            const bool act = T < nvec;
-            decltype(head_dispatch(fam, a, g, 0u, p0)) h0, h1, h2, h3;
-            if (act)
+            const unsigned int stage = k & 1u;
+#pragma unroll
+            for (unsigned int t = 0; t < CH; ++t)
                 {
-                h0 = head_dispatch(fam, a, g, j_cur.x, p0);
-                h1 = head_dispatch(fam, a, g, j_cur.y, p1);
-                h2 = head_dispatch(fam, a, g, j_cur.z, p2);
-                h3 = head_dispatch(fam, a, g, j_cur.w, p3);
+                const bool act = t < rem;
+                decltype(head_dispatch(fam, a, g, 0u, p0)) h0, h1, h2, h3;
+                if (act)
+                    {
+                    h0 = head_dispatch(fam, a, g, j_cur.x, p0);
+                    h1 = head_dispatch(fam, a, g, j_cur.y, p1);
+                    h2 = head_dispatch(fam, a, g, j_cur.z, p2);
+                    h3 = head_dispatch(fam, a, g, j_cur.w, p3);
+                    }
+                if (t + 1u < CH)
+                    {
+                    if (t + 1u < rem)
+                        {
+                        j_cur = ls->read(stage, t + 1u);
+                        p0 = load4(a.pos, j_cur.x);
+                        p1 = load4(a.pos, j_cur.y);
+                        p2 = load4(a.pos, j_cur.z);
+                        p3 = load4(a.pos, j_cur.w);
+                        }
+                    }
+                else
+                    {
+                    const bool more = k + 1u < nchunks; // warp-uniform
+                    if (more)
+                        ls->wait(k + 1u);
+                    if (rem > CH)
+                        {
+                        j_cur = ls->read(stage ^ 1u, 0u);
+                        p0 = load4(a.pos, j_cur.x);
+                        p1 = load4(a.pos, j_cur.y);
+                        p2 = load4(a.pos, j_cur.z);
+                        p3 = load4(a.pos, j_cur.w);
+                        }
+                    if (more)
+                        {
+                        __syncwarp();
+                        ls->issue(stage, src + 2u * CH, rem > 2u * CH ? min(rem - 2u * CH, CH) : 0u);
+                        }
+                    }
+                if (act)
+                    {
+                    body_dispatch(fam, a, h0);
+                    body_dispatch(fam, a, h1);
+                    body_dispatch(fam, a, h2);
+                    body_dispatch(fam, a, h3);
+                    split_trip_dispatch(fam, a, g);
+                    }
                 }
-            const unsigned int Tn = T + 1u;
-            const unsigned int kn = Tn / CH, tn = Tn % CH;
-            if (tn == 0u && Tn < nvec_max)
-                ls->wait(kn); // warp-uniform
-            if (Tn < nvec)
-                {
-                j_cur = ls->read(kn % ListStage::STAGES, tn);
-                p0 = load4(a.pos, j_cur.x);
-                p1 = load4(a.pos, j_cur.y);
-                p2 = load4(a.pos, j_cur.z);
-                p3 = load4(a.pos, j_cur.w);
-                }
-            if (tn == 0u && Tn < nvec_max)
-                {
-                // chunk kn - 1 is consumed (its last indices were read one trip ago): refill its
-                // stage with chunk kn + 1
-                __syncwarp();
-                ls->issue((kn + 1u) % ListStage::STAGES, src + CH * (kn + 1u), count_of(kn + 1u));
-                }
-            if (act)
-                {
-                body_dispatch(fam, a, h0);
-                body_dispatch(fam, a, h1);
-                body_dispatch(fam, a, h2);
-                body_dispatch(fam, a, h3);
-                split_trip_dispatch(fam, a, g);
-                }
+            rem = rem > CH ? rem - CH : 0u;
+            src += CH;
             }
 #if AZP_STAGE_LIST == 2
         asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -1775,8 +1797,16 @@ AZP_D void process_row(Fam& fam,
 // ONE_LANE: the main pass compiled for threads_per_particle = 1 (the launch shape of every dense
 // configuration): the lane stride of the neighbour loop, the shuffle reductions and the group
 // broadcasts fold away at compile time instead of being re-derived from tpp_log2 every trip.
+// The staged one-lane kernels are compiled for blocks of at most 256 threads and three resident
+// blocks, which caps them at 80 registers (six 128-thread blocks per SM, like the unstaged loop).
+#if AZP_STAGE_LIST != 0
+#define AZP_ROW_KERNEL_BOUNDS(Fam, ONE_LANE) \
+    __launch_bounds__((ONE_LANE && Fam::PIPE == 2 && sizeof(typename Fam::S) == 4) ? 256u : max_block<typename Fam::S>(), (ONE_LANE && Fam::PIPE == 2 && sizeof(typename Fam::S) == 4) ? 3 : 1)
+#else
+#define AZP_ROW_KERNEL_BOUNDS(Fam, ONE_LANE) __launch_bounds__(max_block<typename Fam::S>())
+#endif
 template<class Fam, bool LONGPASS, bool ONE_LANE = false>
-__global__ void __launch_bounds__(max_block<typename Fam::S>())
+__global__ void AZP_ROW_KERNEL_BOUNDS(Fam, ONE_LANE)
     row_kernel(const __grid_constant__ KernelArgs<typename Fam::S> a,
                const typename Fam::E::param_type* __restrict__ params,
                const unsigned int tpp_log2_arg)

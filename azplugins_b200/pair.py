@@ -249,6 +249,35 @@ class Pair:
             n_max=self.nlist.n_max,
             **extra)
 
+    def _args_all_rows(self, timestep, compute_virial):
+        """The argument struct of a launch over all rows, rebuilt only when something it points
+        at has changed. Filling ``azp_pair_args`` field by field from Python (tensor views, box
+        conversion, ~30 ctypes stores) costs more host time than the C1 kernel runs (N = 32,000:
+        0.015 ms); a time step that changes nothing but ``timestep`` reuses the struct. Potentials
+        with per-step extra arguments (DPD: kT(t), velocities; aniso: orientations) always take
+        the full path."""
+        if type(self)._extra_args is not Pair._extra_args:
+            return self._args(timestep, compute_virial)
+        st = self._state
+        if st is None:
+            raise RuntimeError("potential is not attached to a State")
+        if self._uploaded_version != self._tables_version:
+            self._upload_tables()
+        nl = self.nlist
+        nl.compute(st)
+        b = st.box
+        key = (st.pos.data_ptr(), nl.n_neigh.data_ptr(), nl.nlist.data_ptr(), nl.head_list.data_ptr(),
+               nl.size, nl.n_max, bool(compute_virial), self._launch_shape, self._mode,
+               self._uploaded_version, st.N, self._force.data_ptr(), b.Lx, b.Ly, b.Lz, b.xy, b.xz,
+               b.yz, b.periodic)
+        cached = getattr(self, "_args_cache", None)
+        if cached is None or cached[0] != key:
+            cached = (key, self._args(timestep, compute_virial))
+            self._args_cache = cached
+        args = cached[1]
+        args.timestep = st.timestep if timestep is None else int(timestep)
+        return args
+
     def compute(self, timestep=None, compute_virial=True, row_ids=None, rows=None):
         """``ForceCompute::compute(timestep)``: enqueue the kernel on the current stream.
         ``row_ids`` (int32 device tensor) restricts the evaluation to those rows (scheduler use:
@@ -256,11 +285,18 @@ class Pair:
         ``(lo, hi)`` to a contiguous range (used by :meth:`compute_to_host`)."""
         if row_ids is not None and rows is not None:
             raise ValueError("give row_ids or rows, not both")
-        args = self._args(timestep, compute_virial, row_ids, rows)
+        if row_ids is None and rows is None:
+            args = self._args_all_rows(timestep, compute_virial)
+        else:
+            args = self._args(timestep, compute_virial, row_ids, rows)
         if args.N == 0:
             return self
-        with torch.cuda.device(self._state.device):
+        dev = self._state.device
+        if torch.cuda.current_device() == dev.index:
             kernels.launch(self._family, self._evaluator, self._bits, args, self._d_params.data_ptr())
+        else:
+            with torch.cuda.device(dev):
+                kernels.launch(self._family, self._evaluator, self._bits, args, self._d_params.data_ptr())
         if row_ids is None and rows is None:
             self._computed_at = (self._state.timestep if timestep is None else int(timestep),
                                  self._tables_version)

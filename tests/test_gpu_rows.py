@@ -231,3 +231,51 @@ def test_device_sfc_sort_matches_host_morton_order():
     f_after = plj2.attach(state).compute()._force.cpu().numpy()
     scale = np.abs(f_before[:, :3]).max()
     assert np.abs(f_after[:, :3] - f_before[perm, :3]).max() < 2e-5 * scale
+
+
+def test_cached_launch_arguments_follow_every_change():
+    """pair.Pair.compute() reuses the argument struct of the previous all-rows launch while
+    nothing it points at has changed (pair.py, _args_all_rows): positions updated in place,
+    a new launch shape, a new mode, new parameters and a rebuilt list must all reach the kernel.
+    The check is a second potential object on the SAME neighbour list, set up from scratch each
+    time (full argument path), evaluated first so that both see the same list."""
+    import torch
+
+    import azplugins_b200 as az
+    from azplugins_b200 import synth
+
+    wl = synth.config2(N=20000)
+    state = wl.make_state(dtype=np.float32)
+    nl = az.nlist.Cell(buffer=synth.BUFFER)
+    (pot,) = wl.make_potentials(nl)
+    pot.attach(state)
+    pot.compute(compute_virial=True)
+
+    def check(**kw):
+        (p2,) = wl.make_potentials(nl)
+        p2.mode = pot.mode
+        for key in list(pot.params.keys()):
+            p2.params[key] = pot.params[key]
+        p2.attach(state)
+        p2.kernel_parameters = pot.kernel_parameters
+        p2.compute(compute_virial=True, **kw)
+        pot.compute(compute_virial=True, **kw)  # cached struct whenever nothing changed
+        assert torch.equal(pot._force, p2._force) and torch.equal(pot._virial, p2._virial)
+        assert float(pot._force.abs().max()) > 0
+        return pot._force.clone()
+
+    f0 = check()
+    f1 = check()
+    assert torch.equal(f0, f1)
+    # positions moved in place (same pointer)
+    state.pos[:, 0] += 0.01 * torch.sin(torch.arange(state.N, device=state.pos.device, dtype=torch.float32))
+    f2 = check()
+    assert not torch.equal(f2, f1)
+    pot.kernel_parameters = (64, 4)
+    check()
+    pot.mode = "none"
+    f3 = check()
+    pot.params[("A", "B")] = dict(epsilon=2.5, kappa=1.1, delta=0.1)
+    f4 = check()
+    assert not torch.equal(f4[:, :3], f3[:, :3])
+    check(timestep=17)

@@ -91,7 +91,10 @@ def main():
         "kernels": [r[name_i][:120] for r in sel],
         "dram_bytes": total("dram__bytes_read.sum", True) + total("dram__bytes_write.sum", True),
         "warp_instructions": total("smsp__inst_executed.sum"),
-        "gpu_time_us_under_ncu": total("gpu__time_duration.sum"),
+        "gpu_time_us_under_ncu": sum(
+            num(r[col["gpu__time_duration.sum"]])
+            * {"ns": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3, "s": 1e6}.get(units[col["gpu__time_duration.sum"]], 1.0)
+            for r in sel),
         "l1_hit_pct": num(main_launch[col["l1tex__t_sector_hit_rate.pct"]]),
         "l2_hit_pct": num(main_launch[col["lts__t_sector_hit_rate.pct"]]),
         "issue_active_pct": num(main_launch[col["smsp__issue_active.avg.pct_of_peak_sustained_active"]]),
