@@ -35,6 +35,10 @@ template<class S> class PairEvaluatorColloid : public PairEvaluatorBase<S>
         ColloidColloid = 2
         };
 
+    // k and asq are what the two light forms need of (A, sigma, a): hoisted per type pair with
+    // the reference's own operation order, so the per-pair results keep their bits --
+    //   point-point:  k = A sigma^6 / 36               (reference :105, an IEEE division per pair)
+    //   sphere-point: k = sigma^3 A a a^2, asq = a^2   (reference :127-135), asq3 = a^2 / 3 (:148)
     struct alignas(16) cache_type
         {
         S A;
@@ -44,6 +48,9 @@ template<class S> class PairEvaluatorColloid : public PairEvaluatorBase<S>
         S aj;
         S e_cut;
         int coupling;
+        S k;
+        S asq;
+        S asq3;
         };
 
     // ---- the three couplings; `force` selects whether force_divr is produced -------------
@@ -55,7 +62,7 @@ template<class S> class PairEvaluatorColloid : public PairEvaluatorBase<S>
         const S r2inv = S(1.0) / rsq;
 #endif
         const S r6inv = r2inv * r2inv * r2inv;
-        const S c1 = c.A * c.sigma_6 / S(36.0);
+        const S c1 = c.k;
         if (force)
             fdr = S(6.0) * c1 * r2inv * r6inv * (S(2.0) * c.sigma_6 * r6inv - S(1.0));
         return c1 * r6inv * (c.sigma_6 * r6inv - S(1.0));
@@ -63,8 +70,7 @@ template<class S> class PairEvaluatorColloid : public PairEvaluatorBase<S>
 
     template<bool force> AZP_HD static S colloidSolvent(const cache_type& c, S rsq, S& fdr)
         {
-        const S a = (c.ai > c.aj) ? c.ai : c.aj;
-        const S asq = a * a;
+        const S asq = c.asq;
         const S d = asq - rsq;
         const S r4 = rsq * rsq;
         const S d3 = d * d * d;
@@ -78,7 +84,7 @@ template<class S> class PairEvaluatorColloid : public PairEvaluatorBase<S>
         const S d6inv = S(1.0) / d6;
         const S dinv = S(1.0) / d;
 #endif
-        const S fR = c.sigma_3 * c.A * a * asq * d3inv;
+        const S fR = c.k * d3inv;
         if (force)
             {
             fdr = S(4.0 / 15.0) * fR
@@ -89,7 +95,7 @@ template<class S> class PairEvaluatorColloid : public PairEvaluatorBase<S>
             }
         return S(2.0 / 9.0) * fR
                * (S(1.0)
-                  - (asq * (asq * (asq / S(3.0) + S(3.0) * rsq) + S(4.2) * r4) + rsq * r4)
+                  - (asq * (asq * (c.asq3 + S(3.0) * rsq) + S(4.2) * r4) + rsq * r4)
                         * c.sigma_6 * d6inv);
         }
 
@@ -145,6 +151,16 @@ template<class S> class PairEvaluatorColloid : public PairEvaluatorBase<S>
             c.coupling = ColloidColloid;
         else
             c.coupling = ColloidSolvent;
+        c.k = S(0), c.asq = S(0), c.asq3 = S(0);
+        if (c.coupling == SolventSolvent)
+            c.k = c.A * c.sigma_6 / S(36.0);
+        else if (c.coupling == ColloidSolvent)
+            {
+            const S a = (c.ai > c.aj) ? c.ai : c.aj;
+            c.asq = a * a;
+            c.asq3 = c.asq / S(3.0);
+            c.k = c.sigma_3 * c.A * a * c.asq;
+            }
         c.e_cut = S(0);
         if (energy_shift && p.A != S(0))
             {

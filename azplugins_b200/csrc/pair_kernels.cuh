@@ -781,7 +781,9 @@ template<class E_, class S_, bool XPLOR, bool VIRIAL, int NTM_> struct IsoFamily
             // -- the whole warp skips the evaluation and the accumulation with one uniform branch.
             // Evaluators opt in with kWarpVote (the vote costs two issue slots per neighbour,
             // which the cheap dense-fluid potentials, PLJ and Yukawa, do not get back).
-            if (E::kWarpVote && __ballot_sync(__activemask(), inside) == 0u)
+            // (not in the in-place loop of a split row: its forms are the light ones and in a
+            // dense fluid the vote never skips)
+            if (E::kWarpVote && !INPLACE_OF_SPLIT && __ballot_sync(__activemask(), inside) == 0u)
                 return;
             const Cache c = TABLE ? types.tab.cache(t_tab) : types.cache(tj);
             S f = S(0), e = S(0);
