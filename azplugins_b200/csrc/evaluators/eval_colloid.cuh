@@ -271,6 +271,7 @@ template<class S> struct IsoTraits<PairEvaluatorColloid<S>>
 #else
     static constexpr bool register_tables = true;
 #endif
+    static constexpr int one_lane_cap = 0;
     };
 #endif
     } // namespace azp

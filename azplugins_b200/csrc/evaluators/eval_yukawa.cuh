@@ -117,5 +117,15 @@ template<class S> class PairEvaluatorExpandedYukawa : public PairEvaluatorBase<S
     private:
     const cache_type& c;
     };
+#ifdef AZP_YUKAWA_REG_CAP
+// A/B: cap the one-lane kernel of this evaluator at 72 / 80 registers (pair_kernels.cuh, OneLaneCap)
+template<class E> struct IsoTraits;
+template<class S> struct IsoTraits<PairEvaluatorExpandedYukawa<S>>
+    {
+    static constexpr int pipe = 2;
+    static constexpr bool register_tables = true;
+    static constexpr int one_lane_cap = AZP_YUKAWA_REG_CAP;
+    };
+#endif
     } // namespace azp
 #endif

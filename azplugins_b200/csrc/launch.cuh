@@ -200,7 +200,7 @@ inline cudaError_t launch_rows(KernelArgs<typename Fam::S> k, const void* d_para
     const size_t smem = Fam::smem_bytes(ntp, s.block);
 #ifndef AZP_NO_ONE_LANE
     // (the staged one-lane kernels are built for blocks of at most 256 threads)
-    if (s.tpp_log2 == 0 && !(AZP_STAGE_LIST != 0 && Fam::PIPE == 2 && sizeof(typename Fam::S) == 4 && s.block > 256u))
+    if (s.tpp_log2 == 0 && s.block <= row_kernel_max_threads<Fam, true>())
         {
         auto kernel = row_kernel<Fam, false, true>;
         // the staged neighbour-list ring (ListStage) sits behind the family's own tables

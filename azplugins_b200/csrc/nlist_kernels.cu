@@ -379,12 +379,12 @@ template<class S, bool FILL> static int rows(const azp_nlist_args* a, cudaStream
     if ((unsigned long long)k.row_offset + k.n_rows > a->N)
         return (int)cudaErrorInvalidValue;
     // lanes per row (a cell is swept TPP candidates at a time). Measured on B200 (C2, 30
-    // candidates per cell, N = 1 M, rebuild reusing the capacities): 2 lanes 2.9 ms, 4 lanes 3.0,
-    // 16 lanes 4.8, 32 lanes 5.2 -- the sweep is instruction bound, so the fewest lanes that
-    // still coalesce pairs of 16-byte candidate loads win
+    // candidates per cell, N = 1 M, rebuild reusing the capacities, two runs): 4 lanes 3.0 / 3.3 ms,
+    // 16 lanes 4.8 / 4.0, 32 lanes 5.2 / 4.7; 2 and 8 lanes were each fastest-but-one in one run
+    // (2.9, 3.4) and 2.3x slower in the other (7.7, 7.6), so the default is 4
     unsigned int tpp = a->threads_per_row;
     if (tpp == 0)
-        tpp = 2u;
+        tpp = 4u;
     switch (tpp)
         {
     case 1:

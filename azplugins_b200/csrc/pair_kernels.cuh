@@ -609,6 +609,7 @@ template<class E> struct IsoTraits
     {
     static constexpr int pipe = 2;
     static constexpr bool register_tables = true;
+    static constexpr int one_lane_cap = 0; // register cap of the one-lane main pass (OneLaneCap)
     };
 
 template<class E_, class S_, bool XPLOR, bool VIRIAL, int NTM_> struct IsoFamily
@@ -1191,12 +1192,15 @@ template<class E_, class S_, bool VIRIAL, int NTM_> struct AnisoFamily
     // registers here and is 50 % slower (0.69 vs 0.46 ms per 4 M particles) than hiding the
     // latency with occupancy (58 registers, 8 CTAs per SM)
     static constexpr int PIPE = 0;
-    // Deferred accept (AcceptQueue) for the two-patch Morse family. Round 1 measured it 6 %
-    // slower than evaluating in place (-11 % instructions, but one exposed gather latency per
-    // heavy round); with all gathers of a round issued together and two queued neighbours per
-    // lane and round it is 3.4 % faster (C5, 4 M particles: 0.454 -> 0.439 ms), so it is on.
+    // Deferred accept (AcceptQueue) for the two-patch Morse family: off. Round 1 measured it
+    // 6 % slower than evaluating in place (-11 % instructions, but one exposed gather latency
+    // per heavy round). Round 2, with all gathers of a round issued together and two queued
+    // neighbours per lane and round (AZP_ANISO_HEAVY_UNROLL): 0.454 -> 0.439 ms at 4 M
+    // particles but 1.746 -> 1.733 ms (0.7 %) at the full 16 M, and a row's sum then depends on
+    // when its warp drains (row ranges are no longer bit-identical to the full launch), so the
+    // in-place evaluation stays.
 #ifndef AZP_ANISO_QUEUE
-#define AZP_ANISO_QUEUE 1
+#define AZP_ANISO_QUEUE 0
 #endif
     static constexpr bool QUEUE = AZP_ANISO_QUEUE != 0;
     static constexpr bool MULTIROW = AZP_ROWS_PER_GROUP > 1;
@@ -1799,14 +1803,27 @@ AZP_D void process_row(Fam& fam,
 // ONE_LANE: the main pass compiled for threads_per_particle = 1 (the launch shape of every dense
 // configuration): the lane stride of the neighbour loop, the shuffle reductions and the group
 // broadcasts fold away at compile time instead of being re-derived from tpp_log2 every trip.
-// The staged one-lane kernels are compiled for blocks of at most 256 threads and three resident
-// blocks, which caps them at 80 registers (six 128-thread blocks per SM, like the unstaged loop).
-#if AZP_STAGE_LIST != 0
-#define AZP_ROW_KERNEL_BOUNDS(Fam, ONE_LANE) \
-    __launch_bounds__((ONE_LANE && Fam::PIPE == 2 && sizeof(typename Fam::S) == 4) ? 256u : max_block<typename Fam::S>(), (ONE_LANE && Fam::PIPE == 2 && sizeof(typename Fam::S) == 4) ? 3 : 1)
-#else
-#define AZP_ROW_KERNEL_BOUNDS(Fam, ONE_LANE) __launch_bounds__(max_block<typename Fam::S>())
-#endif
+// Register cap of the one-lane main pass, per evaluator (IsoTraits<E>::one_lane_cap): 0 = none
+// (launch bounds of the generic kernel), 80 = built for blocks of at most 256 threads with three
+// of them resident, 72 = blocks of at most 128 threads with seven resident. A capped kernel
+// only takes the block sizes it was built for (launch.cuh routes the others to the generic one).
+template<class Fam> struct OneLaneCap
+    {
+    static constexpr int value = 0;
+    };
+template<class E, class S, bool X, bool V, int N> struct OneLaneCap<IsoFamily<E, S, X, V, N>>
+    {
+    static constexpr int value = sizeof(S) == 4 ? IsoTraits<E>::one_lane_cap : 0;
+    };
+template<class Fam, bool ONE_LANE> constexpr unsigned int row_kernel_max_threads()
+    {
+    return !ONE_LANE || OneLaneCap<Fam>::value == 0 ? max_block<typename Fam::S>() : (OneLaneCap<Fam>::value == 72 ? 128u : 256u);
+    }
+template<class Fam, bool ONE_LANE> constexpr unsigned int row_kernel_min_blocks()
+    {
+    return !ONE_LANE || OneLaneCap<Fam>::value == 0 ? 0u : (OneLaneCap<Fam>::value == 72 ? 7u : 3u); // 0 = unspecified
+    }
+#define AZP_ROW_KERNEL_BOUNDS(Fam, ONE_LANE) __launch_bounds__(row_kernel_max_threads<Fam, ONE_LANE>(), row_kernel_min_blocks<Fam, ONE_LANE>())
 template<class Fam, bool LONGPASS, bool ONE_LANE = false>
 __global__ void AZP_ROW_KERNEL_BOUNDS(Fam, ONE_LANE)
     row_kernel(const __grid_constant__ KernelArgs<typename Fam::S> a,
