@@ -17,6 +17,44 @@
 
 namespace azp
     {
+// Scratch of the builder (sort keys, cub temporaries): stream-ordered allocations from a PRIVATE
+// memory pool whose release threshold is unlimited. The default pool gives freed memory back to
+// the driver at the next synchronisation (threshold 0), so every rebuild paid the physical
+// allocation again -- measured: 28-46 ms per rebuild at N = 32,000, where the kernels take
+// 0.2 ms. A private pool leaves the host application's allocator policy alone.
+static cudaError_t scratch_alloc(void** p, size_t bytes, cudaStream_t st)
+    {
+    static cudaMemPool_t pools[64] = {};
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess)
+        return err;
+    if (dev < 0 || dev >= 64)
+        return cudaMallocAsync(p, bytes, st);
+    if (!pools[dev])
+        {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        cudaMemPool_t pool = nullptr;
+        err = cudaMemPoolCreate(&pool, &props);
+        if (err != cudaSuccess)
+            {
+            cudaGetLastError();
+            return cudaMallocAsync(p, bytes, st);
+            }
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        pools[dev] = pool;
+        }
+    return cudaMallocFromPoolAsync(p, bytes, pools[dev], st);
+    }
+    } // namespace azp
+
+namespace azp
+    {
 struct CellGrid
     {
     unsigned int dim[3];
@@ -319,10 +357,10 @@ template<class S> static int bin(const azp_nlist_args* a, cudaStream_t st)
     unsigned int *iota = nullptr, *sorted_cells = nullptr;
     void* temp = nullptr;
     size_t temp_bytes = 0;
-    cudaError_t err = cudaMallocAsync(&iota, sizeof(unsigned int) * a->N, st);
+    cudaError_t err = scratch_alloc((void**)&iota, sizeof(unsigned int) * a->N, st);
     if (err != cudaSuccess)
         return (int)err;
-    err = cudaMallocAsync(&sorted_cells, sizeof(unsigned int) * a->N, st);
+    err = scratch_alloc((void**)&sorted_cells, sizeof(unsigned int) * a->N, st);
     if (err != cudaSuccess)
         {
         cudaFreeAsync(iota, st);
@@ -334,7 +372,7 @@ template<class S> static int bin(const azp_nlist_args* a, cudaStream_t st)
     while ((1ull << bits) < (unsigned long long)ncells + 1 && bits < 32)
         ++bits;
     cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, a->d_cell_of, sorted_cells, iota, a->d_cell_order, (int)a->N, 0, bits, st);
-    err = cudaMallocAsync(&temp, temp_bytes, st);
+    err = scratch_alloc(&temp, temp_bytes, st);
     if (err == cudaSuccess)
         {
         cub::DeviceRadixSort::SortPairs(temp, temp_bytes, a->d_cell_of, sorted_cells, iota, a->d_cell_order, (int)a->N, 0, bits, st);
@@ -458,7 +496,7 @@ template<class S> static int sfc_order(const void* d_pos, const azp_box* box, un
     unsigned int *keys = nullptr, *keys_out = nullptr, *iota = nullptr;
     void* temp = nullptr;
     size_t temp_bytes = 0;
-    cudaError_t err = cudaMallocAsync(&keys, 3 * sizeof(unsigned int) * (size_t)N, st);
+    cudaError_t err = scratch_alloc((void**)&keys, 3 * sizeof(unsigned int) * (size_t)N, st);
     if (err != cudaSuccess)
         return (int)err;
     keys_out = keys + N;
@@ -466,7 +504,7 @@ template<class S> static int sfc_order(const void* d_pos, const azp_box* box, un
     const unsigned int block = 256;
     sfc_keys<S><<<(N + block - 1) / block, block, 0, st>>>(static_cast<const S*>(d_pos), nlist_box<S>(*box), N, keys, iota);
     cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, keys, keys_out, iota, d_order, (int)N, 0, 30, st);
-    err = cudaMallocAsync(&temp, temp_bytes, st);
+    err = scratch_alloc(&temp, temp_bytes, st);
     if (err == cudaSuccess)
         {
         cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys, keys_out, iota, d_order, (int)N, 0, 30, st);

@@ -191,6 +191,13 @@ class Integrator:
                 continue
             # the graph holds device addresses: capture again only when a rebuild moved a buffer
             # (rebuilds that reuse the row capacities keep n_neigh / nlist / head_list in place)
+            if any(nl.n_max > 512 for nl in lists):
+                # a rebuild grew a row past the long-row threshold: that pass allocates its queue
+                # on first use, which must not happen inside a capture -- run these steps eagerly
+                for _ in range(quiet):
+                    self._one_step(a, compute_virial)
+                done += quiet
+                continue
             builds = tuple(t.data_ptr() for nl in lists for t in (nl.n_neigh, nl.nlist, nl.head_list))
             if g is None or builds != g_builds:
                 g = self._capture(a, compute_virial, lists)
