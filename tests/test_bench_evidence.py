@@ -1,0 +1,75 @@
+"""Host logic of the measurement chain (no GPU): the ncu-derived constants bench.py reports are
+tied to the kernel sources they were captured with, and the registration tool produces entries
+bench.py accepts."""
+
+import csv
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+
+def test_source_hash_is_stable_and_sensitive(tmp_path):
+    import srchash
+
+    h = srchash.kernel_source_hash()
+    assert h == srchash.kernel_source_hash() and len(h) == 16
+    # the hash covers the files that determine the pair-force SASS
+    base = os.path.join(ROOT, "azplugins_b200", "csrc")
+    for name in ("pair_kernels.cuh", "azp_core.cuh", "launch.cuh", "capi.cu", "Makefile", "inst_yukawa.cu"):
+        assert os.path.exists(os.path.join(base, name))
+
+
+def test_constants_are_reported_only_for_the_sources_they_were_captured_with(monkeypatch):
+    import bench
+    import srchash
+
+    here = srchash.kernel_source_hash()
+    entry, why, h = bench.ncu_constants("C2")
+    assert h == here
+    table = json.load(open(os.path.join(ROOT, "profiles", "ncu_constants.json")))
+    if table["C2"]["kernel_sources"] == here:
+        assert entry is not None and entry["dram_bytes"] > 5e8 and os.path.exists(os.path.join(ROOT, why))
+    else:
+        assert entry is None and "stale" in why
+    # a capture taken with other sources is refused, whatever it says
+    monkeypatch.setattr(srchash, "kernel_source_hash", lambda: "0" * 16)
+    entry, why, h = bench.ncu_constants("C2")
+    assert entry is None and "stale" in why and h == "0" * 16
+    entry, why, _ = bench.ncu_constants("C9")
+    assert entry is None and "no capture" in why
+
+
+def test_registration_tool_sums_the_launches_of_a_step(tmp_path):
+    raw = tmp_path / "raw.csv"
+    hdr = ["ID", "Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+           "smsp__inst_executed.sum", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
+           "smsp__issue_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread"]
+    units = ["", "", "ms", "Gbyte", "Mbyte", "inst", "%", "%", "%", "register/thread"]
+    rows = [["0", "void azp::row_kernel<A, 0, 1>(...)", "1.5", "2.0", "100", "1000", "80", "40", "60", "100"],
+            ["1", "void azp::row_kernel<A, 1, 0>(...)", "0.5", "0.5", "50", "500", "30", "20", "50", "110"],
+            ["2", "void other_kernel(...)", "9", "9", "9", "9", "9", "9", "9", "9"]]
+    with open(raw, "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow(hdr)
+        w.writerow(units)
+        w.writerows(rows)
+    # run the tool on a copy of the repo layout so the committed table is not touched
+    tools = tmp_path / "tools"
+    tools.mkdir()
+    (tmp_path / "profiles").mkdir()
+    src = open(os.path.join(ROOT, "tools", "ncu_summary.py")).read()
+    (tools / "ncu_summary.py").write_text(src)
+    out = tmp_path / "profiles" / "s.csv"
+    subprocess.run([sys.executable, str(tools / "ncu_summary.py"), str(raw), "--register", "CX", "--n", "7",
+                    "--summary", str(out), "--hash", "abc"], check=True, capture_output=True)
+    entry = json.load(open(tmp_path / "profiles" / "ncu_constants.json"))["CX"]
+    assert entry["kernel_sources"] == "abc" and entry["N"] == 7 and len(entry["kernels"]) == 2
+    assert entry["dram_bytes"] == 2.5e9 + 150e6
+    assert entry["warp_instructions"] == 1500
+    assert abs(entry["gpu_time_us_under_ncu"] - 2000.0) < 1e-6  # ms -> us
+    assert entry["registers"] == 100  # of the longest launch
