@@ -18,7 +18,9 @@ CPU baseline, end-to-end number and clocks (contract: task statement section 4).
   headers under the restated HOOMD loop, else the port) on the host cores, bounded row sample;
   the reference arm never imports the product package (no libazp_b200.so in its process);
 * `check` (N > 1): rows of every rank's slice against a single-domain evaluation;
-* `strong_scaling`: BASELINE.json's scaling case, C5 TwoPatchMorse N = 16 M in total, at this N.
+* `strong_scaling`: BASELINE.json's scaling case, C5 TwoPatchMorse N = 16 M in total, at this N;
+* `other_configs` (N = 1): C3 (Colloid + Hertz, 4 M) and C4 (DPD thermostat, 8 M) timed the same
+  way in the same run, each with its own roofline (`--no-strong` skips both extra records).
 """
 
 import argparse
@@ -91,7 +93,7 @@ def parse():
                     help="bracket the timed region with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     ap.add_argument("--no-fuse", action="store_true", help="never use the fused two-potential pass")
     ap.add_argument("--no-strong", action="store_true",
-                    help="skip the C5 N = 16 M strong-scaling record appended to the C2 line")
+                    help="skip the extra records appended to the C2 line (C5 N = 16 M strong scaling; C3 and C4 at N = 1)")
     ap.add_argument("--strong-n", type=int, default=16000000)
     ap.add_argument("--no-tune", action="store_true")
     ap.add_argument("--block", type=int, default=0, help="pin block_size (with --no-tune)")
@@ -606,8 +608,37 @@ def run_b200(args):
             "launch_shape_block_tpp_ms": sj.tuned, "check": sj.check(),
             "note": "BASELINE.json north star: >= 6x at 8 GPUs for N = 16 M; the total N is fixed, "
                     "so the speed-up is this value over the n_gpus = 1 run's"}
+        entry5, why5, _ = ncu_constants("C5")
+        if entry5 is not None and not multi:
+            line["strong_scaling"]["traffic"] = entry5["dram_bytes"]
+            line["strong_scaling"]["ncu_capture"] = why5
         del sj
         torch.cuda.empty_cache()
+
+    # ---- the other single-GPU configurations of BASELINE.json in the same record ----------------
+    # (N = 1 only; C2 stays the line's `value`. One device-resident timing per configuration with
+    # its own roofline, so the driver-run line carries every kernel, not just the headline's.)
+    if not args.no_strong and args.workload == "C2" and not args.n_per_gpu and not multi:
+        others = []
+        for name in ("C3", "C4"):
+            wlx = synth.CONFIGS[name]()
+            oj = Job(wlx, args, torch, dist, dev, rank, world)
+            for _ in range(W):
+                oj.step()
+            o_ms = oj.time_steps(K) / K
+            o_kern = oj.kernel_ms(K) or o_ms
+            o_roof = oj.roofline(o_kern, hbm_peak, peak_src)
+            entry, why, _ = ncu_constants(name)
+            if entry is not None:
+                o_roof["traffic"] = entry["dram_bytes"]
+            o_roof["ncu_capture"] = why
+            others.append({"workload": wlx.name, "N": wlx.N, "ms_per_step": o_ms,
+                           "value": wlx.N / (o_ms * 1e-3), "unit": UNIT, "roofline": o_roof,
+                           "launch_shape_block_tpp_ms": oj.tuned, "fusion": oj.fusion,
+                           "compute_virial": oj.virial, "potentials": [p["cls"] for p in wlx.potentials]})
+            del oj
+            torch.cuda.empty_cache()
+        line["other_configs"] = others
 
     if rank == 0 and not multi and not args.no_cpu_baseline:
         from azplugins_b200.state import pack_pos
