@@ -56,19 +56,26 @@ def ncu_constants(workload):
     """dram__bytes_read.sum + dram__bytes_write.sum and smsp__inst_executed.sum per launch of the
     dominant kernel, from the committed `ncu --set full` capture of this workload
     (profiles/ncu_constants.json, written by tools/ncu_summary.py --register). A capture taken
-    with other kernel sources than the ones this run was built from is NOT reported: the entry
-    carries the source hash at capture time (tools/srchash.py) and must match."""
+    with other kernels than the ones this run loads is NOT reported: the entry carries the SASS
+    digest of the workload's kernels and the hash of the kernel sources at capture time
+    (tools/srchash.py); the SASS digest must match when both sides have one (a change to another
+    evaluator's kernels then leaves this capture valid), else the source hash must."""
     sys.path.insert(0, os.path.join(ROOT, "tools"))
-    from srchash import kernel_source_hash
+    import srchash
 
     path = os.path.join(ROOT, "profiles", "ncu_constants.json")
-    here = kernel_source_hash()
+    here = srchash.kernel_source_hash()
     if not os.path.exists(path):
         return None, "no capture registered", here
     entry = json.load(open(path)).get(workload)
     if entry is None:
         return None, "no capture registered for %s" % workload, here
-    if entry.get("kernel_sources") != here:
+    sass_here = srchash.kernel_sass_hashes().get(workload)
+    if sass_here and entry.get("kernel_sass"):
+        if entry["kernel_sass"] != sass_here:
+            return None, ("stale capture %s (kernel SASS %s, this build %s)"
+                          % (entry.get("summary"), entry["kernel_sass"], sass_here)), here
+    elif entry.get("kernel_sources") != here:
         return None, ("stale capture %s (kernel sources %s, this build %s)"
                       % (entry.get("summary"), entry.get("kernel_sources"), here)), here
     return entry, entry.get("summary"), here
@@ -557,6 +564,9 @@ def run_b200(args):
     entry, ncu_note, src_hash = ncu_constants(args.workload)
     roofline["ncu_capture"] = ncu_note
     roofline["kernel_sources"] = src_hash
+    import srchash  # tools/ is on the path since ncu_constants()
+
+    roofline["kernel_sass"] = srchash.kernel_sass_hashes().get(args.workload)
     if entry is not None and not multi and n_total == int(entry["N"]):
         roofline["traffic"] = entry["dram_bytes"]
         roofline["traffic_over_algorithmic"] = entry["dram_bytes"] / roofline["algorithmic_bytes_per_step"]

@@ -24,24 +24,46 @@ def test_source_hash_is_stable_and_sensitive(tmp_path):
         assert os.path.exists(os.path.join(base, name))
 
 
-def test_constants_are_reported_only_for_the_sources_they_were_captured_with(monkeypatch):
+def test_constants_are_reported_only_for_the_kernels_they_were_captured_with(monkeypatch):
     import bench
     import srchash
 
     here = srchash.kernel_source_hash()
+    table = json.load(open(os.path.join(ROOT, "profiles", "ncu_constants.json")))
+    # no SASS table for the loaded library: the source hash decides
+    monkeypatch.setattr(srchash, "kernel_sass_hashes", lambda lib_path=None: {})
     entry, why, h = bench.ncu_constants("C2")
     assert h == here
-    table = json.load(open(os.path.join(ROOT, "profiles", "ncu_constants.json")))
     if table["C2"]["kernel_sources"] == here:
         assert entry is not None and entry["dram_bytes"] > 5e8 and os.path.exists(os.path.join(ROOT, why))
     else:
         assert entry is None and "stale" in why
-    # a capture taken with other sources is refused, whatever it says
     monkeypatch.setattr(srchash, "kernel_source_hash", lambda: "0" * 16)
     entry, why, h = bench.ncu_constants("C2")
     assert entry is None and "stale" in why and h == "0" * 16
+    # with a SASS table the digest of THIS workload's kernels decides, whatever the sources say:
+    # an edit that leaves the workload's SASS alone keeps its capture, any other digest loses it
+    monkeypatch.setattr(srchash, "kernel_sass_hashes", lambda lib_path=None: {"C2": table["C2"]["kernel_sass"]})
+    entry, why, _ = bench.ncu_constants("C2")
+    assert entry is not None
+    monkeypatch.setattr(srchash, "kernel_sass_hashes", lambda lib_path=None: {"C2": "f" * 16})
+    entry, why, _ = bench.ncu_constants("C2")
+    assert entry is None and "SASS" in why
     entry, why, _ = bench.ncu_constants("C9")
     assert entry is None and "no capture" in why
+
+
+def test_sass_table_is_bound_to_the_library_file(tmp_path, monkeypatch):
+    import srchash
+
+    side = tmp_path / "sass_hashes.json"
+    lib = tmp_path / "lib.so"
+    lib.write_bytes(b"one build")
+    monkeypatch.setattr(srchash, "SIDECAR", str(side))
+    side.write_text(json.dumps({"library_sha256": srchash._file_digest(str(lib)), "sass": {"C2": "abc"}}))
+    assert srchash.kernel_sass_hashes(str(lib)) == {"C2": "abc"}
+    lib.write_bytes(b"another build")
+    assert srchash.kernel_sass_hashes(str(lib)) == {}
 
 
 def test_registration_tool_sums_the_launches_of_a_step(tmp_path):
@@ -66,9 +88,10 @@ def test_registration_tool_sums_the_launches_of_a_step(tmp_path):
     (tools / "ncu_summary.py").write_text(src)
     out = tmp_path / "profiles" / "s.csv"
     subprocess.run([sys.executable, str(tools / "ncu_summary.py"), str(raw), "--register", "CX", "--n", "7",
-                    "--summary", str(out), "--hash", "abc"], check=True, capture_output=True)
+                    "--summary", str(out), "--hash", "abc", "--sass-hash", "def"], check=True, capture_output=True)
     entry = json.load(open(tmp_path / "profiles" / "ncu_constants.json"))["CX"]
-    assert entry["kernel_sources"] == "abc" and entry["N"] == 7 and len(entry["kernels"]) == 2
+    assert entry["kernel_sources"] == "abc" and entry["kernel_sass"] == "def"
+    assert entry["N"] == 7 and len(entry["kernels"]) == 2
     assert entry["dram_bytes"] == 2.5e9 + 150e6
     assert entry["warp_instructions"] == 1500
     assert abs(entry["gpu_time_us_under_ncu"] - 2000.0) < 1e-6  # ms -> us

@@ -57,6 +57,7 @@ def main():
     ap.add_argument("--n", type=int, default=0)
     ap.add_argument("--summary", default="")
     ap.add_argument("--hash", default="")
+    ap.add_argument("--sass-hash", default="", help="SASS digest of the workload's kernels at capture time")
     ap.add_argument("--match", default="row_kernel")
     ap.add_argument("--launches", default="", help="comma-separated launch indices forming one step")
     a = ap.parse_args()
@@ -87,7 +88,7 @@ def main():
 
     main_launch = max(sel, key=lambda r: num(r[col["gpu__time_duration.sum"]]))
     entry = {
-        "summary": a.summary, "kernel_sources": a.hash, "N": a.n,
+        "summary": a.summary, "kernel_sources": a.hash, "kernel_sass": a.sass_hash, "N": a.n,
         "kernels": [r[name_i][:120] for r in sel],
         "dram_bytes": total("dram__bytes_read.sum", True) + total("dram__bytes_write.sum", True),
         "warp_instructions": total("smsp__inst_executed.sum"),

@@ -9,5 +9,6 @@ TAG=$1; shift
 declare -A N=( [C1]=32000 [C2]=1000000 [C3]=3999766 [C4]=8000000 [C5]=16000000 )
 for WL in "$@"; do
   python tools/ncu_summary.py gpurun_out/${TAG}_${WL}_raw.csv --register $WL --n ${N[$WL]} \
-      --summary profiles/${TAG}_${WL}_ncu_full_summary.csv --hash $(cat gpurun_out/${TAG}_${WL}.srchash)
+      --summary profiles/${TAG}_${WL}_ncu_full_summary.csv --hash $(cat gpurun_out/${TAG}_${WL}.srchash) \
+      --sass-hash "$(cat gpurun_out/${TAG}_${WL}.sasshash 2>/dev/null)"
 done
