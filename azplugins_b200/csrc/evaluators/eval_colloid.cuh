@@ -257,7 +257,14 @@ template<class S> class PairEvaluatorColloid : public PairEvaluatorBase<S>
     private:
     const cache_type& c;
     };
-#if defined(AZP_COLLOID_PIPE0) || defined(AZP_COLLOID_SMEM)
+// Tuning traits of the isotropic family for this evaluator. AZP_COLLOID_CAP=96 caps the one-lane
+// kernel at 96 registers (five 128-thread CTAs per SM instead of four at its natural 106; 12
+// bytes of spills outside the neighbour loop). Measured on C3 (profiles/ab/r02d_ab_c3_cap96.json):
+// main pass 1.312 -> 1.266 ms in the tuner's back-to-back timing, but the step (Colloid and
+// Hertz launches alternating) 1.438 -> 1.448 ms -- no gain, so the default is uncapped.
+#ifndef AZP_COLLOID_CAP
+#define AZP_COLLOID_CAP 0
+#endif
 template<class E> struct IsoTraits;
 template<class S> struct IsoTraits<PairEvaluatorColloid<S>>
     {
@@ -271,8 +278,7 @@ template<class S> struct IsoTraits<PairEvaluatorColloid<S>>
 #else
     static constexpr bool register_tables = true;
 #endif
-    static constexpr int one_lane_cap = 0;
+    static constexpr int one_lane_cap = AZP_COLLOID_CAP;
     };
-#endif
     } // namespace azp
 #endif

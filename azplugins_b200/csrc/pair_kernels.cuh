@@ -1805,8 +1805,9 @@ AZP_D void process_row(Fam& fam,
 // broadcasts fold away at compile time instead of being re-derived from tpp_log2 every trip.
 // Register cap of the one-lane main pass, per evaluator (IsoTraits<E>::one_lane_cap): 0 = none
 // (launch bounds of the generic kernel), 80 = built for blocks of at most 256 threads with three
-// of them resident, 72 = blocks of at most 128 threads with seven resident. A capped kernel
-// only takes the block sizes it was built for (launch.cuh routes the others to the generic one).
+// of them resident, 96 / 72 = blocks of at most 128 threads with five / seven resident. A capped
+// kernel only takes the block sizes it was built for (launch.cuh routes the others to the
+// generic one).
 template<class Fam> struct OneLaneCap
     {
     static constexpr int value = 0;
@@ -1817,11 +1818,12 @@ template<class E, class S, bool X, bool V, int N> struct OneLaneCap<IsoFamily<E,
     };
 template<class Fam, bool ONE_LANE> constexpr unsigned int row_kernel_max_threads()
     {
-    return !ONE_LANE || OneLaneCap<Fam>::value == 0 ? max_block<typename Fam::S>() : (OneLaneCap<Fam>::value == 72 ? 128u : 256u);
+    return !ONE_LANE || OneLaneCap<Fam>::value == 0 ? max_block<typename Fam::S>() : (OneLaneCap<Fam>::value == 80 ? 256u : 128u);
     }
 template<class Fam, bool ONE_LANE> constexpr unsigned int row_kernel_min_blocks()
     {
-    return !ONE_LANE || OneLaneCap<Fam>::value == 0 ? 0u : (OneLaneCap<Fam>::value == 72 ? 7u : 3u); // 0 = unspecified
+    return !ONE_LANE || OneLaneCap<Fam>::value == 0 ? 0u // 0 = unspecified
+                                                       : (OneLaneCap<Fam>::value == 72 ? 7u : (OneLaneCap<Fam>::value == 96 ? 5u : 3u));
     }
 #define AZP_ROW_KERNEL_BOUNDS(Fam, ONE_LANE) __launch_bounds__(row_kernel_max_threads<Fam, ONE_LANE>(), row_kernel_min_blocks<Fam, ONE_LANE>())
 template<class Fam, bool LONGPASS, bool ONE_LANE = false>
