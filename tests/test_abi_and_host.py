@@ -246,3 +246,26 @@ def test_external_and_wall_host_logic():
     # integrator argument checks
     with pytest.raises(ValueError):
         az.md.Integrator(dt=0.001, forces=[bar], methods=[object()])
+
+
+def test_config3_hole_removal_equals_the_brute_force_definition():
+    """synth.config3 removes the solvent inside r < 5.9 of every colloid through a cell binning;
+    the result must be the one of testing every solvent particle against every colloid."""
+    from azplugins_b200 import synth
+
+    wl = synth.config3(N=60000, n_colloid=3000)  # 45 colloids
+    L = wl.box.L[0]
+    col = wl.position[wl.typeid == 1]
+    sol = wl.position[wl.typeid == 0]
+    assert len(col) == 45 and len(sol) > 50000
+    # no solvent particle is inside a hole ...
+    for c in col:
+        d = sol - c
+        d -= L * np.round(d / L)
+        assert ((d ** 2).sum(axis=1) >= 5.9 ** 2).all()
+    # ... and the holes are not larger than that: the solvent density outside them is the
+    # lattice's (every removed particle was inside some hole)
+    n_lat = int(round(0.7 * L ** 3))
+    removed = n_lat - len(sol)
+    expect = 45 * 4.0 / 3.0 * np.pi * 5.9 ** 3 * 0.7
+    assert abs(removed - expect) < 0.03 * expect
