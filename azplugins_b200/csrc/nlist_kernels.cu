@@ -14,6 +14,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include <cmath>
+#include <cstdlib>
 
 namespace azp
     {
@@ -77,6 +78,8 @@ template<class S> struct NlistArgs
     S* cell_pos;     // positions in cell order (contiguous per cell)
     S* pos_at_build; // optional copy of pos for the displacement check
     CellGrid grid;
+    S r_list_max; // largest list cutoff: bounds the stencil of the fine-grid sweep
+    bool fine;    // half-width cells (see nlist_rows_fine)
     unsigned int row_offset;
     unsigned int n_rows;
     const unsigned int* capacity; // FILL only: reuse of the previous build's row capacities
@@ -320,6 +323,18 @@ template<class S> static NlistArgs<S> convert(const azp_nlist_args& a)
         k.grid.dim[d] = a.cell_dim[d];
         k.grid.reach[d] = a.cell_dim[d] >= 3 ? 1 : 0;
         }
+    // fine grid (azp_nlist_cell_dim chose half-width cells): orthorhombic, fully periodic, at
+    // least five cells per axis, cells narrower than the list cutoff but two of them span it
+    k.r_list_max = S(a.r_list_max);
+    k.fine = a.box.tilt[0] == 0.0 && a.box.tilt[1] == 0.0 && a.box.tilt[2] == 0.0;
+    for (int d = 0; d < 3; ++d)
+        {
+        const double w = a.box.L[d] / double(a.cell_dim[d]);
+        k.fine = k.fine && a.box.periodic[d] && a.cell_dim[d] >= 5 && w < a.r_list_max && 2.0 * w >= a.r_list_max;
+        }
+    if (k.fine)
+        for (int d = 0; d < 3; ++d)
+            k.grid.reach[d] = 2;
     k.rlistsq = static_cast<const S*>(a.d_rlistsq);
     k.n_neigh = a.d_n_neigh;
     k.head_list = a.d_head_list;
@@ -386,11 +401,161 @@ template<class S> static int bin(const azp_nlist_args* a, cudaStream_t st)
     return (int)err;
     }
 
+// Fine-grid sweep: cells HALF the list cutoff wide (orthorhombic, fully periodic boxes with at
+// least five such cells per axis). The 5 x 5 x 5 stencil is pruned per particle: for every (z, y)
+// offset the distance from the particle to the slab of cells bounds what is left of r_list^2 for
+// x, and only the cells of that x interval are swept -- as ONE contiguous run of the cell-sorted
+// positions (cells that differ only in x are neighbours in memory), plus one more run when the
+// interval wraps around the box. About a third of the candidates of the 27 full-width cells
+// remain. The bounds carry a slack of 1e-5 L (fp32) for the rounding of the fractional
+// coordinates, so no pair inside r_list can be pruned; the exact test on every candidate, the
+// image update, the ordered append and the capacity logic are those of nlist_rows. The 25 (z, y)
+// offsets are walked by every group of the warp together (the trip counts are warp-uniform).
+template<class S, bool FILL, unsigned int TPP> __global__ void __launch_bounds__(128) nlist_rows_fine(const NlistArgs<S> a)
+    {
+    __shared__ S s_rlistsq[64];
+    const bool small_table = a.ntypes <= 8u;
+    if (small_table)
+        {
+        for (unsigned int t = threadIdx.x; t < a.ntypes * a.ntypes; t += blockDim.x)
+            s_rlistsq[t] = a.rlistsq[t];
+        __syncthreads();
+        }
+    const unsigned int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned int lane = gtid & (TPP - 1u);
+    const unsigned int r = gtid / TPP;
+    const bool active = r < a.n_rows;
+    const unsigned int i = active ? r + a.row_offset : 0u;
+    const Vec4<S> pi = load4(a.pos, i);
+    const unsigned int ti = min(scalar_as_uint(pi.w), a.ntypes - 1u);
+    const BoxDim<S>& b = a.box;
+    const int dim[3] = {(int)a.grid.dim[0], (int)a.grid.dim[1], (int)a.grid.dim[2]};
+    // grid coordinates of particle i: cell c, position g inside the grid (same arithmetic as
+    // cell_coords for an orthorhombic box)
+    const S pq[3] = {pi.x, pi.y, pi.z};
+    S g[3], w[3], slack[3];
+    int c[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+        {
+        S f = pq[d] * b.Linv[d] + S(0.5);
+        f -= floor(f);
+        g[d] = f * S(dim[d]);
+        c[d] = max(0, min(dim[d] - 1, (int)floor(g[d])));
+        w[d] = b.L[d] / S(dim[d]);
+        slack[d] = b.L[d] * (sizeof(S) == 4 ? S(1e-5) : S(1e-12));
+        }
+    const S rmax = a.r_list_max;
+    const S rmaxsq = rmax * rmax;
+    unsigned int count = 0;
+    unsigned int* row = (FILL && active) ? a.nlist + a.head_list[r] : nullptr;
+    const unsigned int cap = (FILL && a.capacity && active) ? a.capacity[r] : 0xffffffffu;
+    const unsigned int group_shift = (threadIdx.x & 31u) & ~(TPP - 1u);
+    const unsigned int group_mask = TPP == 32u ? 0xffffffffu : ((1u << TPP) - 1u);
+    for (int oz = -2; oz <= 2; ++oz)
+        {
+        // lower bound of |z_i - z_j| for any j in the slab of cells c_z + o_z
+        S dz = oz == 0 ? S(0) : (oz > 0 ? (S(c[2] + oz) - g[2]) : (g[2] - S(c[2] + oz + 1))) * w[2] - slack[2];
+        dz = fmax(dz, S(0));
+        int cz = c[2] + oz;
+        S imgz = S(0);
+        if (cz < 0)
+            cz += dim[2], imgz = S(-1);
+        else if (cz >= dim[2])
+            cz -= dim[2], imgz = S(1);
+        for (int oy = -2; oy <= 2; ++oy)
+            {
+            S dy = oy == 0 ? S(0) : (oy > 0 ? (S(c[1] + oy) - g[1]) : (g[1] - S(c[1] + oy + 1))) * w[1] - slack[1];
+            dy = fmax(dy, S(0));
+            int cy = c[1] + oy;
+            S imgy = S(0);
+            if (cy < 0)
+                cy += dim[1], imgy = S(-1);
+            else if (cy >= dim[1])
+                cy -= dim[1], imgy = S(1);
+            const S remsq = rmaxsq - dz * dz - dy * dy;
+            const bool reach_row = active && remsq >= S(0);
+            // x interval of cells that can hold a neighbour, within the 5-cell stencil
+            int xlo = 1, xhi = 0; // empty
+            if (reach_row)
+                {
+                const S rx = (::sqrt(remsq) + slack[0]) / w[0];
+                xlo = max(c[0] - 2, (int)floor(g[0] - rx));
+                xhi = min(c[0] + 2, (int)floor(g[0] + rx));
+                }
+            const unsigned int line = ((unsigned int)cz * a.grid.dim[1] + (unsigned int)cy) * a.grid.dim[0];
+            // two runs: the cells inside [0, dim) and the cells that wrapped (below 0 OR above
+            // dim - 1: with at least five cells per axis a 5-cell interval cannot do both)
+#pragma unroll
+            for (int seg = 0; seg < 2; ++seg)
+                {
+                int a0, a1;
+                S imgx = S(0);
+                if (seg == 0)
+                    a0 = max(xlo, 0), a1 = min(xhi, dim[0] - 1);
+                else if (xlo < 0)
+                    a0 = xlo + dim[0], a1 = min(xhi, -1) + dim[0], imgx = S(-1);
+                else
+                    a0 = max(xlo, dim[0]) - dim[0], a1 = xhi - dim[0], imgx = S(1);
+                unsigned int s0 = 0, s1 = 0;
+                if (reach_row && a0 <= a1)
+                    s0 = a.cell_start[line + (unsigned int)a0], s1 = a.cell_start[line + (unsigned int)a1 + 1u];
+                const unsigned int trips = __reduce_max_sync(0xffffffffu, (s1 - s0 + TPP - 1u) / TPP);
+                for (unsigned int k = 0; k < trips; ++k)
+                    {
+                    const unsigned int s = s0 + k * TPP + lane;
+                    bool pass = false;
+                    unsigned int j = 0;
+                    if (s < s1)
+                        {
+                        const Vec4<S> pj = load4(a.cell_pos, s);
+                        S x = pi.x - pj.x, y = pi.y - pj.y, z = pi.z - pj.z;
+                        x -= b.L[0] * imgx;
+                        y -= b.L[1] * imgy;
+                        z -= b.L[2] * imgz;
+                        const S rsq = x * x + y * y + z * z;
+                        const unsigned int tj = min(scalar_as_uint(pj.w), a.ntypes - 1u);
+                        const unsigned int tp = index2d(a.ntypes, ti, tj);
+                        if (rsq < (small_table ? s_rlistsq[tp] : a.rlistsq[tp]))
+                            {
+                            j = a.cell_order[s];
+                            pass = j != i;
+                            }
+                        }
+                    const unsigned int votes = (__ballot_sync(0xffffffffu, pass) >> group_shift) & group_mask;
+                    if (pass)
+                        {
+                        const unsigned int slot = count + __popc(votes & ((1u << lane) - 1u));
+                        if (FILL && slot < cap)
+                            row[slot] = j;
+                        }
+                    count += __popc(votes);
+                    }
+                }
+            }
+        }
+    if (!active || lane != 0)
+        return;
+    if (!FILL)
+        a.n_neigh[r] = count;
+    else if (a.capacity)
+        {
+        a.n_neigh[r] = min(count, cap);
+        if (count > cap)
+            atomicMax(a.overflow, 1u);
+        }
+    }
+
 template<class S, bool FILL, unsigned int TPP> static int rows_tpp(const NlistArgs<S>& k, cudaStream_t st)
     {
     const unsigned int block = 128;
     const unsigned long long threads = (unsigned long long)k.n_rows * TPP;
     const unsigned int grid = (unsigned int)((threads + block - 1) / block);
+    if (k.fine)
+        {
+        nlist_rows_fine<S, FILL, TPP><<<grid, block, 0, st>>>(k);
+        return (int)cudaGetLastError();
+        }
     // a non-periodic axis has image 0 for every stencil cell that is not skipped, and an axis
     // with a single cell (reach 0) needs rint(): both keep the general sequence
     bool ortho = k.box.xy == S(0) && k.box.xz == S(0) && k.box.yz == S(0);
@@ -416,13 +581,13 @@ template<class S, bool FILL> static int rows(const azp_nlist_args* a, cudaStream
     const NlistArgs<S> k = convert<S>(*a);
     if ((unsigned long long)k.row_offset + k.n_rows > a->N)
         return (int)cudaErrorInvalidValue;
-    // lanes per row (a cell is swept TPP candidates at a time). Measured on B200 (C2, 30
-    // candidates per cell, N = 1 M, rebuild reusing the capacities, two runs): 4 lanes 3.0 / 3.3 ms,
-    // 16 lanes 4.8 / 4.0, 32 lanes 5.2 / 4.7; 2 and 8 lanes were each fastest-but-one in one run
-    // (2.9, 3.4) and 2.3x slower in the other (7.7, 7.6), so the default is 4
+    // lanes per row (a run of candidates is swept TPP at a time). Measured on B200 with the
+    // fine-grid sweep (rebuild reusing the capacities): C2, N = 1 M: 2 lanes 1.71 ms, 4 lanes 1.78,
+    // 8 lanes 2.14, 16 lanes 2.91; C4, N = 8 M: 2 lanes 4.54 ms, 4 lanes 6.42 -- the sweep is bound
+    // by the ordered append, so the fewest lanes that still pair up the 16-byte candidate loads win
     unsigned int tpp = a->threads_per_row;
     if (tpp == 0)
-        tpp = 4u;
+        tpp = 2u;
     switch (tpp)
         {
     case 1:
@@ -597,6 +762,26 @@ extern "C"
             if (c > 1024u)
                 c = 1024u;
             dim[d] = c;
+            }
+        // Half-width cells for the fine-grid sweep (nlist_rows_fine): orthorhombic, fully periodic
+        // boxes that hold at least five such cells per axis. (A grid capped at 1024 cells keeps
+        // cells at least half the cutoff wide; if it made them as wide as the cutoff the sweep
+        // falls back to the 27-cell one by itself.)
+        const bool ortho = xy == 0.0 && xz == 0.0 && yz == 0.0 && box->periodic[0] && box->periodic[1] && box->periodic[2];
+        if (ortho && getenv("AZP_NLIST_COARSE") == nullptr)
+            {
+            uint32_t fine[3];
+            bool ok = true;
+            for (int d = 0; d < 3; ++d)
+                {
+                const double n = 2.0 * box->L[d] / r_list_max;
+                fine[d] = n > 1024.0 ? 1024u : (uint32_t)n;
+                const double w = box->L[d] / fine[d];
+                ok = ok && fine[d] >= 5u && w < r_list_max && 2.0 * w >= r_list_max;
+                }
+            if (ok)
+                for (int d = 0; d < 3; ++d)
+                    dim[d] = fine[d];
             }
         return 0;
         }
