@@ -279,3 +279,29 @@ def test_cached_launch_arguments_follow_every_change():
     f4 = check()
     assert not torch.equal(f4[:, :3], f3[:, :3])
     check(timestep=17)
+
+
+@pytest.mark.parametrize("cfg,N", [("C2", 27000), ("C4", 24000)])
+def test_builder_row_range_equals_the_rows_of_a_full_build(cfg, N):
+    """``Cell.build(state, rows=(lo, hi))`` -- what a rank of the slice scheduler builds: the rows
+    of particles [lo, hi) searched among ALL particles -- gives exactly rows lo..hi-1 of the full
+    build (fine-grid and 27-cell sweep alike; n_neigh / head_list indexed by row - lo)."""
+    import azplugins_b200 as az
+    from azplugins_b200 import synth
+
+    wl = synth.CONFIGS[cfg](N=N)
+    state = wl.make_state(dtype=np.float32)
+    full = az.nlist.Cell(buffer=synth.BUFFER)
+    wl.make_potentials(full)
+    full.build(state)
+    fn, fl, fh = full.to_numpy()
+    for lo, hi in ((0, 1000), (5000, 5001), (7777, state.N)):
+        part = az.nlist.Cell(buffer=synth.BUFFER)
+        wl.make_potentials(part)
+        part.build(state, rows=(lo, hi))
+        pn, pl, ph = part.to_numpy()
+        assert len(pn) == hi - lo and np.array_equal(pn, fn[lo:hi])
+        for r in range(0, hi - lo, max(1, (hi - lo) // 200)):
+            a = pl[ph[r]:ph[r] + pn[r]]
+            b = fl[fh[lo + r]:fh[lo + r] + fn[lo + r]]
+            assert np.array_equal(a, b), (lo, hi, r)
