@@ -104,14 +104,65 @@ template<class S> AZP_D void cell_coords(const BoxDim<S>& b, const CellGrid& g, 
         }
     }
 
+// Where a particle is binned. The sweeps take the periodic image of a pair from how the candidate's
+// cell was reached, which is only right if cell and position of every particle agree. Per axis:
+// the fractional coordinate f = q / L + 1/2 as ONE fused multiply-add of the RAW position (an
+// explicit fma: every kernel gets the same bits whatever the compiler contracts elsewhere), the
+// whole box lengths k = floor(f) the particle is away from the box (0 on a non-periodic axis),
+// the wrapped coordinate fw = f - k that fixes the cell, and the position with the same k lattice
+// vectors taken off. Cell and position then agree by construction -- also for a particle exactly
+// on a box face, where the rounding of 1 / L decides on which side f falls (fp32, L = 9:
+// -4.5 * Linv + 0.5 = -4e-9 -> k = -1, the particle is binned in the LAST cell at +4.5), for a
+// float64 coordinate that rounded onto the upper face in fp32, and for a particle a step outside
+// the box. Deriving the cell from the shifted position instead would round a second time and can
+// land on the other side. A particle with k = 0 on all axes keeps its position bit for bit.
+template<class S> struct Binned
+    {
+    Vec4<S> p; // in-box image
+    S fw[3];   // wrapped fractional coordinates, [0, 1] (1 only by rounding)
+    };
+
+template<class S> AZP_D Binned<S> bin_particle(const BoxDim<S>& b, const Vec4<S>& p)
+    {
+    const S q[3] = {p.x - b.xy * p.y - (b.xz - b.xy * b.yz) * p.z, p.y - b.yz * p.z, p.z};
+    Binned<S> o;
+    S k[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+        {
+        const S f = fma(q[d], b.Linv[d], S(0.5));
+        k[d] = b.periodic[d] ? floor(f) : S(0);
+        o.fw[d] = f - k[d];
+        }
+    o.p = p;
+    if (k[0] != S(0) || k[1] != S(0) || k[2] != S(0))
+        {
+        // lattice vectors (Lx, 0, 0), (xy Ly, Ly, 0), (xz Lz, yz Lz, Lz)
+        o.p.x -= k[0] * b.L[0] + k[1] * b.xy * b.L[1] + k[2] * b.xz * b.L[2];
+        o.p.y -= k[1] * b.L[1] + k[2] * b.yz * b.L[2];
+        o.p.z -= k[2] * b.L[2];
+        }
+    return o;
+    }
+
+// cell of wrapped fractional coordinates (a non-periodic axis clamps: a particle slightly outside
+// the box on a wall-confined axis stays in the boundary cell, next to its neighbours)
+template<class S> AZP_D void grid_cell(const CellGrid& g, const S fw[3], int c[3])
+    {
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+        c[d] = max(0, min((int)g.dim[d] - 1, (int)floor(fw[d] * S(g.dim[d]))));
+    }
+
 template<class S> __global__ void nlist_assign_cells(const NlistArgs<S> a, unsigned int* iota)
     {
     const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.N)
         return;
     const Vec4<S> p = load4(a.pos, i);
+    const Binned<S> bp = bin_particle(a.box, p);
     int c[3];
-    cell_coords(a.box, a.grid, p.x, p.y, p.z, c);
+    grid_cell(a.grid, bp.fw, c);
     a.cell_of[i] = ((unsigned int)c[2] * a.grid.dim[1] + (unsigned int)c[1]) * a.grid.dim[0] + (unsigned int)c[0];
     iota[i] = i;
     if (a.pos_at_build)
@@ -136,14 +187,15 @@ __global__ void nlist_cell_starts(const unsigned int* sorted_cells, unsigned int
     cell_start[c] = lo;
     }
 
-// cell_pos[s] = pos[cell_order[s]]: the candidates of a cell become one contiguous run of
-// 16-byte elements (a broadcast / coalesced load in the row kernel instead of index -> gather)
+// cell_pos[s] = binned position of particle cell_order[s]: the candidates of a cell become one
+// contiguous run of 16-byte elements (a broadcast / coalesced load in the row kernel instead of
+// index -> gather)
 template<class S> __global__ void nlist_sorted_positions(const NlistArgs<S> a)
     {
     const unsigned int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= a.N)
         return;
-    const Vec4<S> p = load4(a.pos, a.cell_order[s]);
+    const Vec4<S> p = bin_particle(a.box, load4(a.pos, a.cell_order[s])).p;
     store4(a.cell_pos, s, p.x, p.y, p.z, p.w);
     }
 
@@ -178,10 +230,11 @@ template<class S, bool FILL, unsigned int TPP, bool ORTHO> __global__ void __lau
     const unsigned int r = gtid / TPP;
     const bool active = r < a.n_rows;
     const unsigned int i = active ? r + a.row_offset : 0u;
-    const Vec4<S> pi = load4(a.pos, i);
+    const Binned<S> bi = bin_particle(a.box, load4(a.pos, i));
+    const Vec4<S> pi = bi.p;
     const unsigned int ti = min(scalar_as_uint(pi.w), a.ntypes - 1u);
     int c[3];
-    cell_coords(a.box, a.grid, pi.x, pi.y, pi.z, c);
+    grid_cell(a.grid, bi.fw, c);
     unsigned int count = 0;
     unsigned int* row = (FILL && active) ? a.nlist + a.head_list[r] : nullptr;
     const unsigned int cap = (FILL && a.capacity && active) ? a.capacity[r] : 0xffffffffu;
@@ -426,21 +479,18 @@ template<class S, bool FILL, unsigned int TPP> __global__ void __launch_bounds__
     const unsigned int r = gtid / TPP;
     const bool active = r < a.n_rows;
     const unsigned int i = active ? r + a.row_offset : 0u;
-    const Vec4<S> pi = load4(a.pos, i);
+    const Binned<S> bi = bin_particle(a.box, load4(a.pos, i));
+    const Vec4<S> pi = bi.p;
     const unsigned int ti = min(scalar_as_uint(pi.w), a.ntypes - 1u);
     const BoxDim<S>& b = a.box;
     const int dim[3] = {(int)a.grid.dim[0], (int)a.grid.dim[1], (int)a.grid.dim[2]};
-    // grid coordinates of particle i: cell c, position g inside the grid (same arithmetic as
-    // cell_coords for an orthorhombic box)
-    const S pq[3] = {pi.x, pi.y, pi.z};
+    // grid coordinates of particle i: cell c (grid_cell's arithmetic), position g inside the grid
     S g[3], w[3], slack[3];
     int c[3];
 #pragma unroll
     for (int d = 0; d < 3; ++d)
         {
-        S f = pq[d] * b.Linv[d] + S(0.5);
-        f -= floor(f);
-        g[d] = f * S(dim[d]);
+        g[d] = bi.fw[d] * S(dim[d]);
         c[d] = max(0, min(dim[d] - 1, (int)floor(g[d])));
         w[d] = b.L[d] / S(dim[d]);
         slack[d] = b.L[d] * (sizeof(S) == 4 ? S(1e-5) : S(1e-12));

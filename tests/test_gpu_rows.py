@@ -305,3 +305,47 @@ def test_builder_row_range_equals_the_rows_of_a_full_build(cfg, N):
             a = pl[ph[r]:ph[r] + pn[r]]
             b = fl[fh[lo + r]:fh[lo + r] + fn[lo + r]]
             assert np.array_equal(a, b), (lo, hi, r)
+
+
+@pytest.mark.parametrize("L,coarse", [(9.0, False), (30.0, False), (30.0, True)])
+def test_builder_with_particles_on_and_outside_the_box_faces(L, coarse, monkeypatch):
+    """Particles exactly on the upper box face (fp32 rounding puts one there about once per 10 M
+    particles) or one box length outside are binned and swept with their in-box image: the list
+    must be the brute-force minimum-image one. L = 9: fine grid at its smallest (6 half-width
+    cells per axis), L = 30: 20 cells per axis; coarse: the 27-cell sweep (AZP_NLIST_COARSE)."""
+    if coarse:
+        monkeypatch.setenv("AZP_NLIST_COARSE", "1")
+    import azplugins_b200 as az
+
+    rng = np.random.default_rng(5)
+    n = 1500 if L < 10 else 4000
+    xyz = rng.uniform(-0.5, 0.5, size=(n, 3)) * L
+    xyz[:30] = 0.5 * np.float64(np.float32(L)) * rng.choice([-1.0, 1.0], size=(30, 3))  # on faces / corners
+    xyz[30:60] = np.where(rng.random((30, 3)) < 0.5, 0.5 * np.float64(np.float32(L)), xyz[30:60])
+    xyz[60:90, 1] += L   # one box length outside
+    xyz[90:120, 2] -= L
+    box = az.Box.cube(L)
+    # State validates nothing about the box faces; build it from raw arrays
+    state = az.State(box, ["A"], xyz, dtype=np.float32)
+    pos = state.pos.cpu().numpy()[:, :3].astype(np.float64)
+    nl = az.nlist.Cell(buffer=0.4)
+    pot = az.pair.PerturbedLennardJones(nlist=nl, default_r_cut=2.5)
+    pot.params[("A", "A")] = dict(epsilon=1.0, sigma=1.0, attraction_scale_factor=0.5)
+    pot.attach(state)
+    nl.build(state)
+    nn, lst, head = nl.to_numpy()
+    r_list = 2.9
+    missing = extra = 0
+    for i in range(n):
+        d = pos[i] - pos
+        d -= L * np.round(d / L)
+        rsq = (d ** 2).sum(axis=1)
+        rsq[i] = 1e9
+        got = set(int(j) for j in lst[head[i]:head[i] + nn[i]])
+        # pairs within 1e-5 of the list cutoff may fall either way (fp32 displacement of the
+        # wrapped image against float64 here); everything clearly inside must be there
+        must = set(np.nonzero(rsq < (r_list * (1 - 1e-5)) ** 2)[0].tolist())
+        may = set(np.nonzero(rsq < (r_list * (1 + 1e-5)) ** 2)[0].tolist())
+        missing += len(must - got)
+        extra += len(got - may)
+    assert missing == 0 and extra == 0
