@@ -111,29 +111,29 @@ template<class S> class PairEvaluatorColloid : public PairEvaluatorBase<S>
     template<bool force> AZP_HD static S colloidColloid(const cache_type& c, S rsq, S& fdr)
         {
         const S r = ::sqrt(rsq);
-        const S k0 = c.ai * c.aj, k1 = c.ai + c.aj, k2 = c.ai - c.aj;
-        const S k3 = k1 + r, k4 = k1 - r, k5 = k2 + r, k6 = k2 - r;
-        const S k7 = S(1.0) / (k3 * k4);
-        const S k8 = S(1.0) / (k5 * k6);
-        S g0 = inv7(k3), g1 = inv7(k4), g2 = inv7(k5), g3 = inv7(k6);
-        const S h0 = ((k3 + S(5.0) * k1) * k3 + S(30.0) * k0) * g0;
-        const S h1 = ((k4 + S(5.0) * k1) * k4 + S(30.0) * k0) * g1;
-        const S h2 = ((k5 + S(5.0) * k2) * k5 - S(30.0) * k0) * g2;
-        const S h3 = ((k6 + S(5.0) * k2) * k6 - S(30.0) * k0) * g3;
-        g0 *= S(42.0) * k0 / k3 + S(6.0) * k1 + k3;
-        g1 *= S(42.0) * k0 / k4 + S(6.0) * k1 + k4;
-        g2 *= S(-42.0) * k0 / k5 + S(6.0) * k2 + k5;
-        g3 *= S(-42.0) * k0 / k6 + S(6.0) * k2 + k6;
+        const S prod = c.ai * c.aj, sum = c.ai + c.aj, diff = c.ai - c.aj;
+        const S sum_p = sum + r, sum_m = sum - r, diff_p = diff + r, diff_m = diff - r;
+        const S inv_sum = S(1.0) / (sum_p * sum_m);
+        const S inv_diff = S(1.0) / (diff_p * diff_m);
+        S w_sp = inv7(sum_p), w_sm = inv7(sum_m), w_dp = inv7(diff_p), w_dm = inv7(diff_m);
+        const S e_sp = ((sum_p + S(5.0) * sum) * sum_p + S(30.0) * prod) * w_sp;
+        const S e_sm = ((sum_m + S(5.0) * sum) * sum_m + S(30.0) * prod) * w_sm;
+        const S e_dp = ((diff_p + S(5.0) * diff) * diff_p - S(30.0) * prod) * w_dp;
+        const S e_dm = ((diff_m + S(5.0) * diff) * diff_m - S(30.0) * prod) * w_dm;
+        w_sp *= S(42.0) * prod / sum_p + S(6.0) * sum + sum_p;
+        w_sm *= S(42.0) * prod / sum_m + S(6.0) * sum + sum_m;
+        w_dp *= S(-42.0) * prod / diff_p + S(6.0) * diff + diff_p;
+        w_dm *= S(-42.0) * prod / diff_m + S(6.0) * diff + diff_m;
         const S fR = c.A * c.sigma_6 / r / S(37800.0);
-        S eng = fR * (h0 - h1 - h2 + h3);
+        S eng = fR * (e_sp - e_sm - e_dp + e_dm);
         if (force)
             {
-            const S dUR = eng / r + S(5.0) * fR * (g0 + g1 - g2 - g3);
+            const S dUR = eng / r + S(5.0) * fR * (w_sp + w_sm - w_dp - w_dm);
             const S dUA = -c.A / S(3.0) * r
-                          * ((S(2.0) * k0 * k7 + S(1.0)) * k7 + (S(2.0) * k0 * k8 - S(1.0)) * k8);
+                          * ((S(2.0) * prod * inv_sum + S(1.0)) * inv_sum + (S(2.0) * prod * inv_diff - S(1.0)) * inv_diff);
             fdr = (dUR + dUA) / r;
             }
-        eng += c.A / S(6.0) * (S(2.0) * k0 * (k7 + k8) - ::log(k8 / k7));
+        eng += c.A / S(6.0) * (S(2.0) * prod * (inv_sum + inv_diff) - ::log(inv_diff / inv_sum));
         return eng;
         }
 

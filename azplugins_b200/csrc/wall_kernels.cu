@@ -82,28 +82,28 @@ template<class S> struct Colloid
     template<bool FORCE> AZP_D S potential(S& force_divr, S rsq) const
         {
         const S r = root(rsq);
-        const S arinv = div(a, r);
-        const S r_minus_a_inv = div(S(1.0), sub(r, a));
-        const S r_plus_a_inv = div(S(1.0), add(r, a));
-        const S r2_minus_a2_inv = mul(r_minus_a_inv, r_plus_a_inv);
-        const S r_minus_a_inv2 = mul(r_minus_a_inv, r_minus_a_inv);
-        const S r_minus_a_inv6 = mul(mul(r_minus_a_inv2, r_minus_a_inv2), r_minus_a_inv2);
-        const S r_plus_a_inv2 = mul(r_plus_a_inv, r_plus_a_inv);
-        const S r_plus_a_inv6 = mul(mul(r_plus_a_inv2, r_plus_a_inv2), r_plus_a_inv2);
+        const S a_over_r = div(a, r);
+        const S near_inv = div(S(1.0), sub(r, a));
+        const S far_inv = div(S(1.0), add(r, a));
+        const S both_inv = mul(near_inv, far_inv);
+        const S near_inv2 = mul(near_inv, near_inv);
+        const S near_inv6 = mul(mul(near_inv2, near_inv2), near_inv2);
+        const S far_inv2 = mul(far_inv, far_inv);
+        const S far_inv6 = mul(mul(far_inv2, far_inv2), far_inv2);
         if (FORCE)
             {
-            const S arinv8 = mul(S(8.0), arinv);
+            const S a_over_r_x8 = mul(S(8.0), a_over_r);
             force_divr = mul(mul(S(6.0), c_1),
-                             add(mul(mul(sub(arinv8, S(1.0)), r_minus_a_inv2), r_minus_a_inv6),
-                                 mul(mul(add(arinv8, S(1.0)), r_plus_a_inv2), r_plus_a_inv6)));
+                             add(mul(mul(sub(a_over_r_x8, S(1.0)), near_inv2), near_inv6),
+                                 mul(mul(add(a_over_r_x8, S(1.0)), far_inv2), far_inv6)));
             force_divr = sub(force_divr,
-                             mul(c_2, mul(mul(mul(mul(mul(S(4.0), a), a), arinv), r2_minus_a2_inv), r2_minus_a2_inv)));
+                             mul(c_2, mul(mul(mul(mul(mul(S(4.0), a), a), a_over_r), both_inv), both_inv)));
             }
-        const S a7 = mul(S(7.0), a);
-        S energy = mul(c_1, add(mul(mul(sub(a7, r), r_minus_a_inv), r_minus_a_inv6),
-                                mul(mul(add(a7, r), r_plus_a_inv), r_plus_a_inv6)));
-        energy = sub(energy, mul(c_2, add(mul(mul(mul(S(2.0), a), r), r2_minus_a2_inv),
-                                          ln(div(r_plus_a_inv, r_minus_a_inv)))));
+        const S seven_a = mul(S(7.0), a);
+        S energy = mul(c_1, add(mul(mul(sub(seven_a, r), near_inv), near_inv6),
+                                mul(mul(add(seven_a, r), far_inv), far_inv6)));
+        energy = sub(energy, mul(c_2, add(mul(mul(mul(S(2.0), a), r), both_inv),
+                                          ln(div(far_inv, near_inv)))));
         return energy;
         }
     AZP_D bool eval(S rsq, S rcutsq, S& force_divr, S& energy) const
