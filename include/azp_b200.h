@@ -19,7 +19,7 @@
  *   azp_param_size/pack/unpack <- E::param_type(pybind11::dict) / asDict() / toPython(), e.g.
  *                                 src/PairEvaluatorPerturbedLennardJones.h:33-54
  *
- * The C++ shim azplugins_b200/csrc/hoomd_shim.h re-declares the three HOOMD templates on top of
+ * The C++ shim include/azp_hoomd_shim.h re-declares the three HOOMD templates on top of
  * these functions; INTEGRATION.md shows the binding a maintainer adds on the reference side.
  *
  * Conventions
