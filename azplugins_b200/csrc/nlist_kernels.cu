@@ -813,6 +813,22 @@ extern "C"
                 c = 1024u;
             dim[d] = c;
             }
+        // One word of cell_start and one search thread per cell: a dilute system in a huge box
+        // gets at most 2^26 cells (256 MB), with cells wider than the cutoff -- the 27-cell
+        // sweep only needs them no narrower. The BASELINE configurations have 0.26 M (C2) to
+        // 26 M (C5) half-width cells.
+        const unsigned long long max_cells = 1ull << 26;
+        auto total = [](const uint32_t* d) { return (unsigned long long)d[0] * d[1] * d[2]; };
+        for (int pass = 0; pass < 8 && total(dim) > max_cells; ++pass)
+            {
+            const double shrink = 0.999 * cbrt(double(max_cells) / double(total(dim)));
+            for (int d = 0; d < 3; ++d)
+                if (dim[d] >= 3u)
+                    {
+                    const uint32_t c = (uint32_t)(dim[d] * shrink);
+                    dim[d] = c >= 3u ? c : 3u;
+                    }
+            }
         // Half-width cells for the fine-grid sweep (nlist_rows_fine): orthorhombic, fully periodic
         // boxes that hold at least five such cells per axis. (A grid capped at 1024 cells keeps
         // cells at least half the cutoff wide; if it made them as wide as the cutoff the sweep
@@ -829,7 +845,7 @@ extern "C"
                 const double w = box->L[d] / fine[d];
                 ok = ok && fine[d] >= 5u && w < r_list_max && 2.0 * w >= r_list_max;
                 }
-            if (ok)
+            if (ok && total(fine) <= max_cells)
                 for (int d = 0; d < 3; ++d)
                     dim[d] = fine[d];
             }

@@ -183,3 +183,41 @@ def test_box_face_particles_of_the_gpu_test_are_binned_where_they_sit():
         for j in need:
             dd = posb[i] - posb[j] - L * np.array(img[j])
             assert (dd ** 2).sum() < r * r * (1 + 1e-5), (i, j)
+
+
+def _library_dims(L, r, periodic=(True, True, True), tilt=(0.0, 0.0, 0.0)):
+    import ctypes
+
+    import azplugins_b200 as az
+    from azplugins_b200 import _lib
+
+    c = az.Box(L[0], L[1], L[2], *tilt, periodic=periodic).to_c()
+    d = (ctypes.c_uint32 * 3)()
+    assert _lib.lib.azp_nlist_cell_dim(ctypes.byref(c), float(r), d) == 0
+    return [int(x) for x in d]
+
+
+def test_library_grid_choice_matches_the_model_and_caps_the_cell_count():
+    """azp_nlist_cell_dim (host code, no GPU needed): half-width cells where the model says so,
+    full-width cells otherwise, never 2 cells on an axis, and at most 2^26 cells in all (a dilute
+    system in a huge box must not allocate gigabytes of cell_start)."""
+    for L, r in [((126.0, 126.0, 126.0), 3.9), ((298.7, 298.7, 298.7), 2.0), ((9.0, 9.0, 9.0), 2.9),
+                 ((20.0, 31.0, 47.0), 1.7), ((8.0, 8.0, 8.0), 2.9), ((7.0, 30.0, 30.0), 2.9)]:
+        fine = grid_dims(np.array(L), r)
+        got = _library_dims(L, r)
+        if fine is not None:
+            assert got == fine, (L, r)
+        else:
+            assert got == [int(x / r) if x / r >= 3.0 else 1 for x in L], (L, r)
+    # BASELINE sizes stay on the fine grid
+    assert _library_dims((126.0,) * 3, 3.9) == [64, 64, 64]
+    assert _library_dims((298.7,) * 3, 2.0) == [298, 298, 298]
+    # too many half-width cells -> full-width cells; too many of those -> wider cells
+    assert _library_dims((1000.0,) * 3, 3.0) == [333, 333, 333]
+    for L, r in [((2000.0,) * 3, 2.0), ((3000.0, 3000.0, 900.0), 1.0), ((5000.0, 5000.0, 10.0), 2.0)]:
+        d = _library_dims(L, r)
+        assert d[0] * d[1] * d[2] <= 1 << 26 and all(x == 1 or x >= 3 for x in d)
+        assert all(x == 1 or Lx / x >= r for x, Lx in zip(d, L))  # no narrower than the cutoff
+    # a slab (non-periodic z) and a tilted box never take the fine grid
+    assert _library_dims((30.0, 30.0, 30.0), 2.9, periodic=(True, True, False)) == [10, 10, 10]
+    assert _library_dims((30.0, 30.0, 30.0), 2.9, tilt=(0.1, 0.0, 0.0))[2] == 10
