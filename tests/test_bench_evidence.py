@@ -96,3 +96,51 @@ def test_registration_tool_sums_the_launches_of_a_step(tmp_path):
     assert entry["warp_instructions"] == 1500
     assert abs(entry["gpu_time_us_under_ncu"] - 2000.0) < 1e-6  # ms -> us
     assert entry["registers"] == 100  # of the longest launch
+
+
+def test_sass_digest_does_not_depend_on_where_the_tree_is_checked_out(tmp_path, monkeypatch):
+    """cuobjdump names the source file of an object by its absolute path ("identifier = ...");
+    the digest ignores that line, so the library built from another checkout (or rebuilt on the
+    GPU box) still matches the registered captures."""
+    import shutil
+
+    import srchash
+
+    if not (shutil.which("cuobjdump") or os.path.exists("/usr/local/cuda/bin/cuobjdump")):
+        import pytest
+        pytest.skip("no cuobjdump")
+    real_run = subprocess.run
+    seen = []
+
+    def fake_run(cmd, **kw):
+        out = real_run(cmd, **kw)
+        if "-sass" in cmd:
+            seen.append(cmd[-1])
+            assert b"identifier = " in out.stdout
+            out.stdout = out.stdout.replace(b"identifier = /", b"identifier = /some/other/checkout/")
+        return out
+
+    side = tmp_path / "sass_hashes.json"
+    monkeypatch.setattr(srchash, "SIDECAR", str(side))
+    monkeypatch.setattr(srchash, "OBJECTS", {"C1": ["inst_plj.o"]})  # one object: seconds
+    a = srchash.write_sass_hashes()
+    if a is None:
+        import pytest
+        pytest.skip("library objects not built")
+    monkeypatch.setattr(srchash.subprocess, "run", fake_run)
+    b = srchash.write_sass_hashes()
+    assert seen and a["sass"] == b["sass"]
+
+
+def test_registered_captures_belong_to_the_kernels_of_this_build():
+    """The committed ncu captures of C2-C5 were taken with exactly the SASS this tree builds
+    (build() has run before the tests): bench.py will report their DRAM traffic."""
+    import srchash
+
+    here = srchash.kernel_sass_hashes()
+    if not here:
+        import pytest
+        pytest.skip("no SASS table next to the library (build() not run)")
+    table = json.load(open(os.path.join(ROOT, "profiles", "ncu_constants.json")))
+    for wl in ("C2", "C3", "C4", "C5"):
+        assert table[wl]["kernel_sass"] == here[wl], wl

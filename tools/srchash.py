@@ -68,6 +68,9 @@ def write_sass_hashes():
             if not os.path.exists(path):
                 return None
             out = subprocess.run([tool, "-sass", path], capture_output=True, check=True).stdout
+            # the dump names the source file of the object by its absolute path ("identifier =
+            # /root/repo/..."): dropped, so the same SASS built in another checkout hashes the same
+            out = b"\n".join(l for l in out.split(b"\n") if not l.startswith(b"identifier = "))
             h.update(o.encode())
             h.update(out)
         table[wl] = h.hexdigest()[:16]
